@@ -1,0 +1,533 @@
+#!/usr/bin/env python
+"""Benchmark of the gdf hot path on B200 (see DESIGN.md "Measurement").
+
+One JSON line on stdout.  Headline workload (BASELINE.json metric "rows/sec hash inner-join ... int64"):
+C3 = gdf_inner_join of 1e9 probe rows x 1e8 build rows, int64 keys (build = permutation, probe
+uniform, every probe row matches once).  A "step" is one gdf_inner_join call over device-resident
+columns, outputs freed with gdf_column_free.  The same line carries the other two single-GPU
+configs as `workloads` entries: C4 gdf_group_by_sum (1e9 rows, 1e6 int64 groups, Zipf s=1.05) and
+C2 gdf_filter (1e9 int64 rows, 10 % selectivity), each with its own roofline object.
+
+  value      rows/s (probe+build rows per step / device time), inputs resident in HBM
+  e2e        same metric through the same C-ABI call but from pinned HOST buffers: H2D of both key
+             columns and D2H of both index columns inside the timed region
+  roofline   dominant kernel of the headline step: algorithmic bytes of that kernel / its average
+             launch duration (CUDA events recorded by the library around each launch, live in the
+             timed steps) vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the C oracle port (single thread) on a bounded sample of the same workload
+
+--impl reference runs the reference's own kernels (oracle/_ref/libgdf_ref.so = gpuopenanalytics/libgdf
+rebuilt for sm_100a; the reference has no CPU implementation) through the identical harness.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+SEED = 0xabcdef  # reference python/tests/utils.py:31-33
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink every row count (debug only)")
+    ap.add_argument("--only", default="", help="comma list of join,groupby,filter (debug only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# library loading: ours through the package, the reference through the same cdef
+# ------------------------------------------------------------------------------------------------
+class Api(object):
+    def __init__(self, impl):
+        self.impl = impl
+        if impl == "b200":
+            from libgdf_b200.librmm_cffi import librmm, librmm_config
+            librmm_config.use_pool_allocator = True
+            librmm.finalize()
+            librmm.initialize()
+            from libgdf_b200.libgdf_cffi import ffi, libgdf_api
+            self.ffi, self.lib = ffi, libgdf_api
+            self.profile = True
+        else:
+            import cffi
+            from libgdf_b200._cdef import header_cdef
+            path = os.path.join(ROOT, "oracle", "_ref", "libgdf_ref.so")
+            if not os.path.isfile(path):
+                raise FileNotFoundError(path)
+            ffi = cffi.FFI()
+            ffi.cdef(header_cdef("gdf/cffi/types.h", "gdf/cffi/functions.h", "memory.h"))
+            self.ffi, self.lib = ffi, ffi.dlopen(path)
+            opts = ffi.new("rmmOptions_t*")
+            opts.allocation_mode = self.lib.PoolAllocation   # the reference's own test config (conftest.py:7-9)
+            opts.initial_pool_size = 48 << 30
+            opts.enable_logging = False
+            rc = self.lib.rmmInitialize(opts)
+            if rc != 0:
+                raise RuntimeError("reference rmmInitialize -> %d" % rc)
+            self.profile = False
+
+    def check(self, rc, what):
+        if rc != 0:
+            name = self.ffi.string(self.lib.gdf_error_get_name(rc)).decode()
+            raise RuntimeError("%s -> %s" % (what, name))
+
+    def column(self, tensor):
+        ffi, lib = self.ffi, self.lib
+        col = ffi.new("gdf_column*")
+        code = {torch.int64: lib.GDF_INT64, torch.int32: lib.GDF_INT32}[tensor.dtype]
+        lib.gdf_column_view(col, ffi.cast("void*", tensor.data_ptr()), ffi.NULL, tensor.numel(), code)
+        return col
+
+    def profile_begin(self):
+        if self.profile:
+            self.lib.gdfx_profile_enable(1)
+            self.profile_end()
+
+    def profile_end(self):
+        if not self.profile:
+            return {}
+        buf = self.ffi.new("char[]", 1 << 16)
+        self.lib.gdfx_profile_report(buf, 1 << 16)
+        return json.loads(self.ffi.string(buf).decode())
+
+
+def alias(ffi, cdata_ptr, n, np_dtype):
+    class _A(object):
+        pass
+    a = _A()
+    a.__cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(np_dtype).str,
+                                  "data": (int(ffi.cast("uintptr_t", cdata_ptr)), False), "version": 2, "strides": None}
+    return torch.as_tensor(a, device="cuda")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------------
+class Clocks(object):
+    """SM clock + throttle reasons sampled through NVML from a background thread while the timed
+    regions run.  (An `nvidia-smi -lms` child process was measured to slow every driver call of this
+    process down - a 42 ms join step became 280 ms - so the same counters are read in-process at a
+    low rate instead.)"""
+    PERIOD_S = 0.05
+
+    def __init__(self, index):
+        self.rows, self.stop_flag, self.handle = [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+        except Exception:
+            self.handle = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append((time.perf_counter(), sm, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD_S)
+
+    def window(self, t0, t1):
+        return [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-2:]
+
+    def stop(self):
+        self.stop_flag = True
+
+    def summarise(self, rows):
+        if not rows or self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        sm = sorted(r[1] for r in rows)
+        reasons = [n for n, b in bits.items() if any(r[2] & b for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def gen(seed_offset):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED + seed_offset)
+    return g
+
+
+def timed_steps(fn, warmup, steps):
+    """W untimed + exactly K timed steps, CUDA events on the launching (default) stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    return e0.elapsed_time(e1) / steps, (t0, t1)
+
+
+class JoinWorkload(object):
+    name = "C3 gdf_inner_join 1e9 x 1e8 int64 (build = permutation, probe uniform, 100% hit)"
+
+    def __init__(self, api, scale, rank=0):
+        self.api = api
+        self.B, self.P = int(1e8 * scale), int(1e9 * scale)
+        self.build = torch.randperm(self.B, generator=gen(1 + 1000 * rank), device="cuda", dtype=torch.int64)
+        self.probe = torch.randint(0, self.B, (self.P,), generator=gen(0 + 1000 * rank), device="cuda", dtype=torch.int64)
+        ffi, lib = api.ffi, api.lib
+        self.ctx = ffi.new("gdf_context*")
+        lib.gdf_context_view(self.ctx, 0, lib.GDF_HASH, 0, 0, 0)
+        self.idx = ffi.new("int[]", [0])
+        self.out_l, self.out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
+        self.rows_per_step = self.P + self.B
+        self.pairs = None
+
+    def call(self, probe, build):
+        ffi, lib = self.api.ffi, self.api.lib
+        lc, rc = self.api.column(probe), self.api.column(build)
+        la, ra = ffi.new("gdf_column*[]", [lc]), ffi.new("gdf_column*[]", [rc])
+        self.api.check(lib.gdf_inner_join(la, 1, self.idx, ra, 1, self.idx, 1, 0, ffi.NULL, self.out_l, self.out_r,
+                                          self.ctx), "gdf_inner_join")
+        self.pairs = int(self.out_l.size)
+
+    def free(self):
+        lib = self.api.lib
+        for o in (self.out_l, self.out_r):
+            if o.data != self.api.ffi.NULL:
+                lib.gdf_column_free(o)
+
+    def step(self):
+        self.call(self.probe, self.build)
+        self.free()
+
+    def algorithmic_bytes(self):  # key columns in + int32 index pairs out
+        return 8 * (self.P + self.B) + 8 * self.pairs
+
+    def check(self):
+        """size-independent properties at full size: pair count, every pair joins equal keys,
+        left indices are a permutation of the probe rows (100 % hit, unique build keys)."""
+        self.call(self.probe, self.build)
+        n = self.pairs
+        li = alias(self.api.ffi, self.out_l.data, n, np.int32).long()
+        ri = alias(self.api.ffi, self.out_r.data, n, np.int32).long()
+        ok = n == self.P and bool((self.probe[li] == self.build[ri]).all())
+        ok = ok and int(li.sum().item()) == self.P * (self.P - 1) // 2
+        del li, ri
+        self.free()
+        return ok
+
+    def e2e_setup(self):
+        self.h_probe = torch.empty(self.P, dtype=torch.int64, pin_memory=True)
+        self.h_build = torch.empty(self.B, dtype=torch.int64, pin_memory=True)
+        self.h_probe.copy_(self.probe)
+        self.h_build.copy_(self.build)
+        self.d_probe, self.d_build = torch.empty_like(self.probe), torch.empty_like(self.build)
+        self.h_out_l = torch.empty(self.P, dtype=torch.int32, pin_memory=True)
+        self.h_out_r = torch.empty(self.P, dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+        return 8 * (self.P + self.B), 8 * self.P
+
+    def e2e_step(self):
+        self.d_probe.copy_(self.h_probe, non_blocking=True)
+        self.d_build.copy_(self.h_build, non_blocking=True)
+        self.call(self.d_probe, self.d_build)
+        n = self.pairs
+        self.h_out_l[:n].copy_(alias(self.api.ffi, self.out_l.data, n, np.int32), non_blocking=True)
+        self.h_out_r[:n].copy_(alias(self.api.ffi, self.out_r.data, n, np.int32), non_blocking=True)
+        torch.cuda.synchronize()
+        self.free()
+
+
+class GroupbyWorkload(object):
+    name = "C4 gdf_group_by_sum 1e9 rows, 1e6 int64 groups, Zipf s=1.05, int64 values"
+
+    def __init__(self, api, scale, rows=None):
+        self.api = api
+        self.N = int((rows or 1e9) * scale)
+        self.G = max(int(1e6 * scale), 16)
+        ranks = torch.arange(1, self.G + 1, device="cuda", dtype=torch.float64)
+        cdf = torch.cumsum(ranks.pow(-1.05), 0)
+        cdf /= cdf[-1].clone()
+        ids = torch.randperm(self.G, generator=gen(3), device="cuda", dtype=torch.int64) * 7919 + 13
+        self.keys = torch.empty(self.N, dtype=torch.int64, device="cuda")
+        chunk = 1 << 27
+        g = gen(2)
+        for lo in range(0, self.N, chunk):  # inverse-CDF sampling in chunks (float64 temporaries)
+            hi = min(self.N, lo + chunk)
+            u = torch.rand(hi - lo, generator=g, device="cuda", dtype=torch.float64)
+            self.keys[lo:hi] = ids[torch.searchsorted(cdf, u).clamp_(max=self.G - 1)]
+            del u
+        self.vals = torch.randint(0, 1000, (self.N,), generator=gen(4), device="cuda", dtype=torch.int64)
+        self.out_keys = torch.empty(self.N, dtype=torch.int64, device="cuda")
+        self.out_vals = torch.empty(self.N, dtype=torch.int64, device="cuda")
+        ffi, lib = api.ffi, api.lib
+        self.ctx = ffi.new("gdf_context*")
+        lib.gdf_context_view(self.ctx, 0, lib.GDF_HASH, 0, 0, 0)
+        self.rows_per_step = self.N
+        self.groups = None
+
+    def step(self):
+        ffi, lib = self.api.ffi, self.api.lib
+        k, v = self.api.column(self.keys), self.api.column(self.vals)
+        ok, ov = self.api.column(self.out_keys), self.api.column(self.out_vals)
+        self.api.check(lib.gdf_group_by_sum(1, ffi.new("gdf_column*[]", [k]), v, ffi.NULL,
+                                            ffi.new("gdf_column*[]", [ok]), ov, self.ctx), "gdf_group_by_sum")
+        self.groups = int(ov.size)
+
+    def algorithmic_bytes(self):  # 16 B/row in + 16 B/group out
+        return 16 * self.N + 16 * self.groups
+
+    def check(self):
+        self.step()
+        g = self.groups
+        total_ok = int(self.out_vals[:g].sum().item()) == int(self.vals.sum().item())
+        uniq = torch.unique(self.out_keys[:g]).numel() == g
+        return total_ok and uniq and g == torch.unique(self.keys).numel()
+
+
+class FilterWorkload(object):
+    name = "C2 gdf_filter 1e9 int64 rows uniform [0,10), == 3 (10 % selectivity)"
+
+    def __init__(self, api, scale):
+        self.api = api
+        self.N = int(1e9 * scale)
+        self.col = torch.randint(0, 10, (self.N,), generator=gen(5), device="cuda", dtype=torch.int64)
+        self.d_cols = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.d_types = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.val = torch.tensor([3], dtype=torch.int64, device="cuda")
+        self.d_vals = torch.tensor([self.val.data_ptr()], dtype=torch.int64, device="cuda")
+        self.d_indx = torch.empty(int(self.N * 0.11) + 1024, dtype=torch.int64, device="cuda")
+        self.new_sz = api.ffi.new("size_t*")
+        self.rows_per_step = self.N
+        self.selected = None
+
+    def step(self):
+        ffi, lib = self.api.ffi, self.api.lib
+        cols = ffi.new("gdf_column[]", 1)
+        cols[0] = self.api.column(self.col)[0]
+        self.api.check(lib.gdf_filter(self.N, cols, 1, ffi.cast("void**", self.d_cols.data_ptr()),
+                                      ffi.cast("int*", self.d_types.data_ptr()), ffi.cast("void**", self.d_vals.data_ptr()),
+                                      ffi.cast("size_t*", self.d_indx.data_ptr()), self.new_sz), "gdf_filter")
+        self.selected = int(self.new_sz[0])
+
+    def algorithmic_bytes(self):  # 8 B/row in + 8 B per selected index out
+        return 8 * self.N + 8 * self.selected
+
+    def check(self):
+        self.step()
+        k = self.selected
+        idx = self.d_indx[:k]
+        ok = k == int((self.col == 3).sum().item()) and bool((self.col[idx] == 3).all())
+        return ok and bool((idx[1:] > idx[:-1]).all())
+
+
+def run_workload(api, wl, args, peak_gbs, clocks):
+    api.profile_begin()
+    ms, (t0, t1) = timed_steps(wl.step, args.warmup, args.steps)
+    prof = api.profile_end()
+    # warm-up launches are included in prof: scale to the timed share by launches / (W+K)
+    total_calls = args.warmup + args.steps
+    kernels = {k: {"launches_per_step": v["launches"] / total_calls, "ms_per_step": v["ms"] / total_calls} for k, v in prof.items()}
+    res = {
+        "workload": wl.name, "ms_per_step": ms, "rows_per_step": wl.rows_per_step,
+        "rows_per_s": wl.rows_per_step / (ms * 1e-3),
+        "algorithmic_GB": wl.algorithmic_bytes() / 1e9,
+        "path_GBps": wl.algorithmic_bytes() / 1e9 / (ms * 1e-3),
+        "path_frac_of_measured_hbm": wl.algorithmic_bytes() / 1e9 / (ms * 1e-3) / peak_gbs,
+        "kernels": kernels, "clocks": clocks.summarise(clocks.window(t0, t1)),
+    }
+    return res
+
+
+# per-kernel algorithmic bytes per launch (compulsory reads + writes of THAT kernel), see DESIGN.md
+def kernel_bytes(name, wl):
+    if isinstance(wl, JoinWorkload):
+        P, B, pairs = wl.P, wl.B, wl.pairs
+        table = {"join_part_hist": None, "join_part_scatter": None}
+        if name == "join_part_probe":
+            return 12 * P + 8 * pairs            # {key,row} pairs in, index pairs out
+        if name == "join_part_scatter":
+            return (8 + 12) * (P + B) / 2.0      # two launches per step (build side, probe side): average
+        if name == "join_part_hist":
+            return 8 * (P + B) / 2.0
+        if name == "join_part_build":
+            return 12 * B + 16 * B
+        return table.get(name)
+    if isinstance(wl, GroupbyWorkload):
+        if name == "groupby_build_fast":
+            return 16 * wl.N
+    if isinstance(wl, FilterWorkload):
+        if name == "select":
+            return 8 * wl.N + 8 * wl.selected
+    return None
+
+
+def roofline_for(res, wl, peak_gbs, peak_kind):
+    ks = res["kernels"]
+    if not ks:
+        return None
+    top = max(ks, key=lambda k: ks[k]["ms_per_step"])
+    per_launch_ms = ks[top]["ms_per_step"] / max(ks[top]["launches_per_step"], 1e-9)
+    nbytes = kernel_bytes(top, wl)
+    if nbytes is None:
+        return {"kernel": top, "bound": "hbm", "achieved": None, "peak": peak_gbs, "unit": "GB/s", "frac": None, "traffic": None}
+    achieved = nbytes / 1e9 / (per_launch_ms * 1e-3)
+    return {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_kind,
+            "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": per_launch_ms,
+            "share_of_step": ks[top]["ms_per_step"] / res["ms_per_step"]}
+
+
+def cpu_baseline_join(scale):
+    """C oracle port (oracle/gdf_oracle.c, single thread) on a bounded sample of C3: 2e7 x 2e6."""
+    import oracle
+    rng = np.random.RandomState(SEED % (2 ** 32))
+    B, P = max(int(2e6 * min(scale * 10, 1.0)), 1000), max(int(2e7 * min(scale * 10, 1.0)), 10000)
+    build = rng.permutation(B).astype(np.int64)
+    probe = rng.randint(0, B, P).astype(np.int64)
+    t0 = time.perf_counter()
+    l, r = oracle.join(oracle.JOIN_INNER, [probe], [build])
+    dt = time.perf_counter() - t0
+    assert len(l) == P
+    return {"value": (P + B) / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+            "sample": "C3 shape at %d x %d rows (C oracle port, 1 thread, %.1f s)" % (P, B, dt)}
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    torch.cuda.set_device(local_rank)
+    if world > 1 and args.impl == "b200":
+        from libgdf_b200 import dist
+        return dist.bench_main(args, rank, world, local_rank)
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak_gbs, peak_kind = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak_gbs, peak_kind = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+    try:
+        api = Api(args.impl)
+    except Exception as exc:  # reference library not built
+        print(json.dumps({"impl": args.impl, "unavailable": str(exc)}))
+        return 0
+    only = set(filter(None, args.only.split(",")))
+    clocks = Clocks(local_rank)
+    out = {"metric": "rows_per_sec_hash_inner_join_int64", "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
+           "data": "synthetic (seeded torch device RNG, SURVEY.md 8d)", "impl": args.impl}
+    workloads = {}
+
+    # ---- headline: C3 inner join ----
+    if not only or "join" in only:
+        wl = JoinWorkload(api, args.scale)
+        parity_ok = wl.check()
+        res = run_workload(api, wl, args, peak_gbs, clocks)
+        res["parity_properties_ok"] = parity_ok
+        res["output_pairs"] = wl.pairs
+        out.update({"value": res["rows_per_s"], "ms_per_step": res["ms_per_step"], "clocks": res["clocks"],
+                    "config": {"workload": wl.name, "probe_rows": wl.P, "build_rows": wl.B, "key_dtype": "int64",
+                               "rows_counted": "probe+build", "l2_policy": "inputs (8.8 GB) larger than L2, no flush",
+                               "rmm": "pool"}})
+        roof = roofline_for(res, wl, peak_gbs, peak_kind)
+        if roof:
+            out["roofline"] = roof
+        out["gpu_launches"] = int(round(sum(k["launches_per_step"] for k in res["kernels"].values()) * args.steps)) if res["kernels"] else None
+        if not args.no_e2e:
+            try:
+                h2d, d2h = wl.e2e_setup()
+                e_ms, _ = timed_steps(wl.e2e_step, 1, max(1, min(args.steps, 3)))
+                out["e2e"] = {"value": wl.rows_per_step / (e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "steps": max(1, min(args.steps, 3))}
+                for a in ("h_probe", "h_build", "d_probe", "d_build", "h_out_l", "h_out_r"):
+                    delattr(wl, a)
+            except Exception as exc:
+                out["e2e"] = {"value": None, "unit": "rows/s", "error": str(exc)[:200]}
+        workloads["join"] = res
+        del wl
+        torch.cuda.empty_cache()
+
+    # ---- C4 group-by sum ----
+    if not only or "groupby" in only:
+        try:
+            rows = 5e8 if args.impl == "reference" else None  # reference int overflow above 2^29 rows
+            wl = GroupbyWorkload(api, args.scale, rows)
+            ok = wl.check()
+            res = run_workload(api, wl, args, peak_gbs, clocks)
+            res["parity_properties_ok"] = ok
+            res["groups"] = wl.groups
+            res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind)
+            workloads["groupby"] = res
+            del wl
+        except Exception as exc:
+            workloads["groupby"] = {"error": str(exc)[:300]}
+        torch.cuda.empty_cache()
+
+    # ---- C2 filter ----
+    if not only or "filter" in only:
+        try:
+            wl = FilterWorkload(api, args.scale)
+            ok = wl.check()
+            res = run_workload(api, wl, args, peak_gbs, clocks)
+            res["parity_properties_ok"] = ok
+            res["selected"] = wl.selected
+            res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind)
+            workloads["filter"] = res
+            del wl
+        except Exception as exc:
+            workloads["filter"] = {"error": str(exc)[:300]}
+        torch.cuda.empty_cache()
+    clocks.stop()
+
+    out["workloads"] = workloads
+    if "value" not in out and workloads:   # debug runs with --only
+        first = next(iter(workloads.values()))
+        out.update({"value": first.get("rows_per_s"), "ms_per_step": first.get("ms_per_step"),
+                    "config": {"workload": first.get("workload")}, "clocks": first.get("clocks")})
+    if args.impl == "reference":
+        out["cpu_baseline"] = {"value": out.get("value"), "unit": "rows/s", "cores": 1, "kind": "reference",
+                               "sample": "full workload on the GPU: the reference is a CUDA library with no CPU path; "
+                                         "this arm runs its own kernels rebuilt for sm_100a (oracle/_ref)"}
+    elif not args.no_cpu:
+        try:
+            out["cpu_baseline"] = cpu_baseline_join(args.scale)
+        except Exception as exc:
+            out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "port", "sample": "failed: %s" % exc}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

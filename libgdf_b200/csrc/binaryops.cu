@@ -121,6 +121,7 @@ gdf_error launch_binary(gdf_column* lhs, gdf_column* rhs, gdf_column* output) {
   Tout* o = static_cast<Tout*>(output->data);
   gdf_nvtx_range_push("LIBGDF_BINARY_OP", GDF_YELLOW);
   const int max_blocks = sm_count() * 8;
+  B200_TIMED("binary_op");
   constexpr int VEC = 16 / sizeof(T);
   const bool out_aligned = (reinterpret_cast<uintptr_t>(o) % (sizeof(Tout) * VEC)) == 0;
   if (!lhs->valid && !rhs->valid && aligned16(l) && aligned16(r) && out_aligned) {

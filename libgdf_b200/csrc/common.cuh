@@ -85,6 +85,15 @@ struct Scratch {  // RAII wrapper; frees in stream order
   ~Scratch() { release(); }
 };
 
+// Optional per-kernel timing (gdfx_profile_enable / gdfx_profile_report, include/gdf_b200_ext.h).
+// B200_TIMED("name") brackets the launches in the enclosing scope with events on stream 0.
+struct KernelTimer {
+  explicit KernelTimer(const char* name);
+  ~KernelTimer();
+  int slot;
+};
+#define B200_TIMED(name) ::b200::KernelTimer b200_kernel_timer__(name)
+
 // Small pinned host mailbox for "count" read-backs (one per host thread).
 void* pinned_mailbox();  // >= 256 bytes, cudaHostAlloc'd
 

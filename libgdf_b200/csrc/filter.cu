@@ -164,7 +164,10 @@ gdf_error run_select(const Policy& pol, size_t n, size_t* h_count) {
   B200_CUDA_TRY(cudaMemsetAsync(desc.ptr, 0, tiles * sizeof(uint64_t) + sizeof(unsigned long long), 0));
   uint64_t* d = desc.as<uint64_t>();
   unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + tiles);
-  select_kernel<Policy><<<(unsigned)tiles, select_detail::kThreads>>>(pol, n, d, d_count);
+  {
+    B200_TIMED("select");
+    select_kernel<Policy><<<(unsigned)tiles, select_detail::kThreads>>>(pol, n, d, d_count);
+  }
   B200_CHECK_LAST();
   unsigned long long* box = static_cast<unsigned long long*>(pinned_mailbox());
   B200_REQUIRE(box != nullptr, GDF_CUDA_ERROR);
@@ -306,6 +309,7 @@ gdf_error launch_static(gdf_column* lhs, B value, gdf_column* out, int op) {
     int8_t* o = static_cast<int8_t*>(out->data);
     constexpr int V = 16 / sizeof(A);
     const bool vec_ok = aligned16(l) && (reinterpret_cast<uintptr_t>(o) % V == 0);
+    B200_TIMED("compare_static");
     compare_static_kernel<A, B><<<stream_blocks(n / V / 4 + 1), 256>>>(l, value, o, n, op, vec_ok);
     B200_CHECK_LAST();
   }

@@ -223,71 +223,129 @@ template <typename KT> __device__ __forceinline__ uint32_t hash_key(unsigned lon
   return murmur3_32<sizeof(KT)>(bits);
 }
 
-template <typename KT, typename IT>
-__global__ void __launch_bounds__(kThreads)
-build_fast_kernel(const KT* __restrict__ key_col, const IT* __restrict__ values, RowSource src, int op,
-                  FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt, unsigned mask, unsigned slots,
-                  unsigned probe_limit, Spill spill, int* __restrict__ side_used) {
-  using UK = typename std::conditional<sizeof(KT) == 8, unsigned long long, unsigned>::type;
-  const int fold_op = (op == OP_COUNT || op == OP_AVG) ? OP_SUM : op;
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  const size_t n_round = (src.n + stride - 1) / stride * stride;  // whole warps stay in the loop
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n_round; i += stride) {
-    const bool active = i < src.n;
-    const unsigned amask = __ballot_sync(0xffffffffu, active);
-    if (!active) continue;
-    const size_t r = src.row(i);
-    const unsigned long long key = (unsigned long long)(UK)key_col[r];
-    int64_t v = (op == OP_COUNT) ? 1 : (int64_t)values[r];
-    unsigned long long c = 1;
-    // ---- warp pre-aggregation: lanes holding the same key fold into the lowest such lane, which
-    //      then issues ONE table update for the whole group (a Zipf-hot key costs one L2 atomic
-    //      per warp instead of one per row) ----
-    const unsigned peers = __match_any_sync(amask, key);
-    const int leader = __ffs(peers) - 1;
-    if (peers & (peers - 1)) {
-      unsigned rest = peers & ~(1u << lane_id());
-      int64_t accv = v;
-      while (rest) {  // same trip count for every lane of the group
-        const int from = __ffs(rest) - 1;
-        rest &= rest - 1;
-        const int64_t ov = __shfl_sync(peers, v, from);
-        if (fold_op == OP_MIN) accv = ov < accv ? ov : accv;
-        else if (fold_op == OP_MAX) accv = ov > accv ? ov : accv;
-        else accv += ov;
-        ++c;
-      }
-      v = accv;
+// Fold (v, c) for `key` into the global table.  Returns false if no slot was found within the probe
+// bound (table too small for the number of groups).
+static __device__ __forceinline__ bool global_fold(FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt,
+                                                   unsigned mask, unsigned slots, unsigned probe_limit,
+                                                   unsigned long long key, uint32_t h, int64_t v,
+                                                   unsigned long long c, int fold_op, int* side_used) {
+  if (key == kEmptyKey) {  // a real key equal to the EMPTY pattern lives in the side slot
+    fold(&tab[slots].acc, v, fold_op);
+    if (cnt) atomicAdd(&cnt[slots], c);
+    *side_used = 1;
+    return true;
+  }
+  unsigned s = h & mask;
+  for (unsigned probe = 0; probe < probe_limit; ++probe, s = (s + 1) & mask) {
+    unsigned long long k = tab[s].key;  // plain load: a stale EMPTY only costs a failed CAS
+    if (k == kEmptyKey) {
+      const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
+      k = (prev == kEmptyKey) ? key : prev;
     }
-    int placed = 1;
-    if ((int)lane_id() == leader) {
-      if (key == kEmptyKey) {  // a real key equal to the EMPTY pattern lives in the side slot
-        fold(&tab[slots].acc, v, fold_op);
-        if (cnt) atomicAdd(&cnt[slots], c);
-        *side_used = 1;
-      } else {
-        placed = 0;
-        unsigned s = hash_key<KT>(key) & mask;
-        for (unsigned probe = 0; probe < probe_limit; ++probe, s = (s + 1) & mask) {
-          unsigned long long k = tab[s].key;
-          if (k == kEmptyKey) {
-            const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
-            k = (prev == kEmptyKey) ? key : prev;
+    if (k == key) {
+      fold(&tab[s].acc, v, fold_op);
+      if (cnt) atomicAdd(&cnt[s], c);
+      return true;
+    }
+  }
+  return false;
+}
+
+// 64-bit wrapping add in SHARED memory built from 32-bit atomics: on B200 a 32-bit shared atomic
+// runs ~8x faster than a 64-bit one (profiles/r01_microbench.txt: ~2900 vs ~400 Gop/s), and for
+// small non-negative addends the high word is touched only on a carry.
+static __device__ __forceinline__ void smem_add64(unsigned long long* acc, int64_t v) {
+  unsigned* w = reinterpret_cast<unsigned*>(acc);
+  const unsigned lo = (unsigned)(unsigned long long)v, hi = (unsigned)((unsigned long long)v >> 32);
+  const unsigned old = atomicAdd(&w[0], lo);
+  const unsigned up = hi + (unsigned)((old + lo) < old);
+  if (up) atomicAdd(&w[1], up);
+}
+
+constexpr int kFastThreads = 1024;       // one CTA per SM, the CTA owns the SM's shared memory
+constexpr unsigned kCacheSlots = 8192;   // per-CTA hot-key cache: 8192 x {key 8 B, acc 8 B, cnt 4 B}
+constexpr unsigned kCacheProbes = 4;
+
+struct FastCache {
+  unsigned long long key[kCacheSlots];
+  unsigned long long acc[kCacheSlots];
+  unsigned cnt[kCacheSlots];
+};
+
+// Per-CTA shared-memory aggregation in front of the L2-resident global table.  Every row first tries
+// the CTA's cache (first-come, bounded linear probing); only rows whose key did not get a cache
+// slot go to the global table.  Under a Zipf key distribution the hot keys claim their slots within
+// the first few thousand rows of a CTA and are then folded with shared-memory atomics only - the
+// single hottest key of C4 (9.5 % of all rows) would otherwise serialise ~1e8 same-address L2 atomics.
+// The cache is flushed into the global table once, when the CTA has consumed its share of the rows.
+template <typename KT, typename IT>
+__global__ void __launch_bounds__(kFastThreads, 1)
+build_fast_kernel(const KT* __restrict__ key_col, const IT* __restrict__ values, size_t n, int op,
+                  FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt, unsigned mask, unsigned slots,
+                  unsigned probe_limit, int* __restrict__ flags /*[0]=side slot used, [1]=overflow*/) {
+  using UK = typename std::conditional<sizeof(KT) == 8, unsigned long long, unsigned>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastCache& cache = *reinterpret_cast<FastCache*>(smem_raw);
+  const int fold_op = (op == OP_COUNT || op == OP_AVG) ? OP_SUM : op;
+  const bool additive = fold_op == OP_SUM;
+  const int64_t identity = op == OP_MIN ? (int64_t)std::numeric_limits<IT>::max()
+                                        : (op == OP_MAX ? (int64_t)std::numeric_limits<IT>::lowest() : 0);
+  for (unsigned i = threadIdx.x; i < kCacheSlots; i += kFastThreads) {
+    cache.key[i] = kEmptyKey;
+    cache.acc[i] = (unsigned long long)identity;
+    cache.cnt[i] = 0;
+  }
+  __syncthreads();
+  // contiguous share of rows per CTA, walked with a CTA-wide stride so loads stay coalesced
+  const size_t per = (n + gridDim.x - 1) / gridDim.x;
+  const size_t lo = (size_t)blockIdx.x * per;
+  const size_t hi = lo + per < n ? lo + per : n;
+  constexpr int U = 4;
+  for (size_t base = lo; base < hi; base += (size_t)kFastThreads * U) {
+    unsigned long long k[U];
+    int64_t v[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = base + (size_t)u * kFastThreads + threadIdx.x;
+      live[u] = r < hi;
+      k[u] = live[u] ? (unsigned long long)(UK)key_col[r] : 0ull;
+      v[u] = (live[u] && op != OP_COUNT) ? (int64_t)values[r] : 1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      const uint32_t h = hash_key<KT>(k[u]);
+      bool done = false;
+      if (k[u] != kEmptyKey) {
+        unsigned s = (h >> 7) & (kCacheSlots - 1);  // bits disjoint from the global slot's low bits
+#pragma unroll
+        for (unsigned p = 0; p < kCacheProbes && !done; ++p, s = (s + 1) & (kCacheSlots - 1)) {
+          unsigned long long ck = cache.key[s];
+          if (ck == kEmptyKey) {
+            const unsigned long long prev = atomicCAS(&cache.key[s], kEmptyKey, k[u]);
+            ck = (prev == kEmptyKey) ? k[u] : prev;
           }
-          if (k == key) {
-            fold(&tab[s].acc, v, fold_op);
-            if (cnt) atomicAdd(&cnt[s], c);
-            placed = 1;
-            break;
+          if (ck == k[u]) {
+            if (additive) smem_add64(&cache.acc[s], v[u]);
+            else if (fold_op == OP_MIN) atomicMin(reinterpret_cast<long long*>(&cache.acc[s]), (long long)v[u]);
+            else atomicMax(reinterpret_cast<long long*>(&cache.acc[s]), (long long)v[u]);
+            if (cnt) atomicAdd(&cache.cnt[s], 1u);
+            done = true;
           }
         }
       }
+      if (!done && !global_fold(tab, cnt, mask, slots, probe_limit, k[u], h, v[u], 1ull, fold_op, &flags[0]))
+        flags[1] = 1;
     }
-    placed = __shfl_sync(peers, placed, leader);
-    if (!placed) {  // the whole group failed: every member spills its own row id
-      const unsigned long long at = atomicAdd(spill.count, 1ull);
-      spill.rows[at] = (int32_t)r;
-    }
+  }
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < kCacheSlots; i += kFastThreads) {
+    const unsigned long long ck = cache.key[i];
+    if (ck == kEmptyKey) continue;
+    if (!global_fold(tab, cnt, mask, slots, probe_limit, ck, hash_key<KT>(ck), (int64_t)cache.acc[i],
+                     (unsigned long long)cache.cnt[i], fold_op, &flags[0]))
+      flags[1] = 1;
   }
 }
 
@@ -377,6 +435,7 @@ gdf_error groupby_generic(const TableView& keys, const KeyOut& ko, const void* v
     if (op == OP_MIN) identity = (ACC)std::numeric_limits<A>::max();
     else if (op == OP_MAX) identity = (ACC)std::numeric_limits<A>::lowest();
     else identity = (ACC)0;
+    B200_TIMED("groupby_generic_level");
     init_generic_kernel<ACC><<<grid_for(slots), kThreads>>>(t_rows.as<int32_t>(), t_acc.as<ACC>(),
                                                            t_cnt.as<unsigned long long>(), slots, identity);
     B200_CHECK_LAST();
@@ -403,56 +462,63 @@ gdf_error groupby_generic(const TableView& keys, const KeyOut& ko, const void* v
   return GDF_SUCCESS;
 }
 
-// ---- fast driver: same two-level scheme as the generic path ----
+#include "groupby_fast.cuh"
+
+// ---- fast driver: one bounded, L2-resident table.  If the keys do not fit (more groups than the
+// table can hold within the probe bound) the call reports `overflowed` and the caller reruns the
+// input through the generic two-level path. ----
 template <typename KT, typename IT, typename OT>
 gdf_error groupby_fast(const KT* key_col, size_t n, const void* values, int op, KT* out_keys, void* out_agg,
-                       int out_dtype, size_t* out_groups) {
+                       int out_dtype, size_t* out_groups, bool* overflowed) {
   using VT = typename std::conditional<std::is_same<IT, void>::value, int32_t, IT>::type;
+  *overflowed = false;
   Scratch misc;
   B200_CUDA_TRY(misc.alloc(4 * sizeof(unsigned long long)));
   B200_CUDA_TRY(cudaMemsetAsync(misc.ptr, 0, 4 * sizeof(unsigned long long), 0));
   unsigned long long* cursor = misc.as<unsigned long long>();
-  unsigned long long* spill_count = cursor + 1;
-  int* side_used = reinterpret_cast<int*>(cursor + 2);
+  int* flags = reinterpret_cast<int*>(cursor + 1);
   int64_t identity = 0;
   if (op == OP_MIN) identity = (int64_t)std::numeric_limits<VT>::max();
   if (op == OP_MAX) identity = (int64_t)std::numeric_limits<VT>::lowest();
-
-  Scratch spill_a;
-  RowSource src{nullptr, n};
-  for (int level = 0; level < 2; ++level) {
-    unsigned slots = pow2_at_least(2 * src.n);
-    bool can_spill = false;
-    if (level == 0 && slots > kLevel1Slots) {
-      slots = kLevel1Slots;
-      can_spill = true;
-    }
-    Scratch tab, cnt;
-    B200_CUDA_TRY(tab.alloc(((size_t)slots + 1) * sizeof(FastSlot)));
-    if (op == OP_AVG) B200_CUDA_TRY(cnt.alloc(((size_t)slots + 1) * sizeof(unsigned long long)));
-    Spill spill{nullptr, spill_count};
-    if (can_spill) {
-      B200_CUDA_TRY(spill_a.alloc(src.n * sizeof(int32_t)));
-      spill.rows = spill_a.as<int32_t>();
-    }
+  unsigned slots = pow2_at_least(2 * n);
+  const bool bounded = slots > kLevel1Slots;
+  if (bounded) slots = kLevel1Slots;
+  Scratch tab, cnt;
+  B200_CUDA_TRY(tab.alloc(((size_t)slots + 1) * sizeof(FastSlot)));
+  if (op == OP_AVG) B200_CUDA_TRY(cnt.alloc(((size_t)slots + 1) * sizeof(unsigned long long)));
+  {
+    B200_TIMED("groupby_init_table");
     init_fast_kernel<<<grid_for((size_t)slots + 1), kThreads>>>(tab.as<FastSlot>(), cnt.as<unsigned long long>(),
                                                                (size_t)slots + 1, identity);
-    B200_CHECK_LAST();
-    B200_CUDA_TRY(cudaMemsetAsync(side_used, 0, sizeof(int), 0));
-    build_fast_kernel<KT, VT><<<grid_for(src.n), kThreads>>>(
-        key_col, static_cast<const VT*>(values), src, op, tab.as<FastSlot>(), cnt.as<unsigned long long>(),
-        slots - 1, slots, can_spill ? kProbeLimitL1 : slots, spill, side_used);
-    B200_CHECK_LAST();
-    extract_fast_kernel<KT, VT, OT><<<grid_for((size_t)slots + 1), kThreads>>>(
-        tab.as<FastSlot>(), cnt.as<unsigned long long>(), slots, side_used, op, out_keys, out_agg, out_dtype, cursor);
-    B200_CHECK_LAST();
-    if (!can_spill) break;
-    unsigned long long spilled = 0;
-    gdf_error e = read_count(spill_count, &spilled);
-    if (e != GDF_SUCCESS) return e;
-    if (spilled == 0) break;
-    src = RowSource{spill.rows, (size_t)spilled};
   }
+  B200_CHECK_LAST();
+  auto kern = build_fast_kernel_v3<KT, VT>;
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastCache3)));
+  size_t want = (n + kGrabRows - 1) / kGrabRows;                 // one warp-grab each
+  want = (want + kFastThreads3 / 32 - 1) / (kFastThreads3 / 32);  // CTAs needed
+  const size_t resident = (size_t)sm_count() * 2;
+  const int blocks = (int)(want < resident ? (want ? want : 1) : resident);
+  {
+    B200_TIMED("groupby_build_fast");
+    kern<<<blocks, kFastThreads3, sizeof(FastCache3)>>>(key_col, static_cast<const VT*>(values), n, op,
+                                                       tab.as<FastSlot>(), cnt.as<unsigned long long>(), slots - 1,
+                                                       slots, bounded ? kProbeLimitL1 : slots, flags, cursor + 3);
+  }
+  B200_CHECK_LAST();
+  if (bounded) {
+    int h_flags[2] = {0, 0};
+    B200_CUDA_TRY(cudaMemcpy(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
+    if (h_flags[1]) {
+      *overflowed = true;
+      return GDF_SUCCESS;
+    }
+  }
+  {
+    B200_TIMED("groupby_extract");
+    extract_fast_kernel<KT, VT, OT><<<grid_for((size_t)slots + 1), kThreads>>>(
+        tab.as<FastSlot>(), cnt.as<unsigned long long>(), slots, flags, op, out_keys, out_agg, out_dtype, cursor);
+  }
+  B200_CHECK_LAST();
   unsigned long long groups = 0;
   gdf_error e = read_count(cursor, &groups);
   if (e != GDF_SUCCESS) return e;
@@ -506,7 +572,7 @@ gdf_error dispatch_generic(const TableView& keys, const KeyOut& ko, gdf_column* 
 
 template <typename KT>
 gdf_error dispatch_fast_key(gdf_column* key, gdf_column* col_agg, int op, gdf_column* out_key, gdf_column* out_agg,
-                            size_t* groups, bool* handled) {
+                            size_t* groups, bool* overflowed, bool* handled) {
   *handled = true;
   const KT* k = static_cast<const KT*>(key->data);
   KT* ok = static_cast<KT*>(out_key->data);
@@ -515,12 +581,12 @@ gdf_error dispatch_fast_key(gdf_column* key, gdf_column* col_agg, int op, gdf_co
   void* oa = out_agg->data;
   const int od = out_agg->dtype;
   if (op == OP_COUNT) {
-    if (dtype_width(od) == 4 && integer_storage(od)) return groupby_fast<KT, void, int32_t>(k, n, v, op, ok, oa, od, groups);
-    if (dtype_width(od) == 8 && integer_storage(od)) return groupby_fast<KT, void, int64_t>(k, n, v, op, ok, oa, od, groups);
+    if (dtype_width(od) == 4 && integer_storage(od)) return groupby_fast<KT, void, int32_t>(k, n, v, op, ok, oa, od, groups, overflowed);
+    if (dtype_width(od) == 8 && integer_storage(od)) return groupby_fast<KT, void, int64_t>(k, n, v, op, ok, oa, od, groups, overflowed);
   } else {
     const int id = col_agg->dtype;
-    if (dtype_width(id) == 4 && integer_storage(id)) return groupby_fast<KT, int32_t, int32_t>(k, n, v, op, ok, oa, od, groups);
-    if (dtype_width(id) == 8 && integer_storage(id)) return groupby_fast<KT, int64_t, int64_t>(k, n, v, op, ok, oa, od, groups);
+    if (dtype_width(id) == 4 && integer_storage(id)) return groupby_fast<KT, int32_t, int32_t>(k, n, v, op, ok, oa, od, groups, overflowed);
+    if (dtype_width(id) == 8 && integer_storage(id)) return groupby_fast<KT, int64_t, int64_t>(k, n, v, op, ok, oa, od, groups, overflowed);
   }
   *handled = false;
   return GDF_SUCCESS;
@@ -546,12 +612,12 @@ gdf_error group_by_hash(int ncols, gdf_column** cols, gdf_column* col_agg, gdf_c
   size_t groups = 0;
   bool done = false;
   if (ncols == 1 && integer_storage(cols[0]->dtype) && dtype_width(cols[0]->dtype) >= 4) {
-    bool handled = false;
+    bool handled = false, overflowed = false;
     gdf_error e = dtype_width(cols[0]->dtype) == 8
-                      ? dispatch_fast_key<int64_t>(cols[0], col_agg, op, out_vals[0], out_agg, &groups, &handled)
-                      : dispatch_fast_key<int32_t>(cols[0], col_agg, op, out_vals[0], out_agg, &groups, &handled);
+                      ? dispatch_fast_key<int64_t>(cols[0], col_agg, op, out_vals[0], out_agg, &groups, &overflowed, &handled)
+                      : dispatch_fast_key<int32_t>(cols[0], col_agg, op, out_vals[0], out_agg, &groups, &overflowed, &handled);
     if (e != GDF_SUCCESS) return e;
-    done = handled;
+    done = handled && !overflowed;
   }
   if (!done) {
     TableView keys;

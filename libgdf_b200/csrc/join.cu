@@ -287,6 +287,7 @@ gdf_error generic_hash_join(int kind, const TableView& probe, const TableView& b
   unsigned long long* cursor = misc.as<unsigned long long>();
   int* has_dup = reinterpret_cast<int*>(cursor + 1);
   if (B) {
+    B200_TIMED("join_generic_build");
     build_kernel<<<grid_for(B), kThreads>>>(build, table.as<unsigned long long>(), slots - 1, has_dup);
     B200_CHECK_LAST();
   }
@@ -320,6 +321,7 @@ gdf_error generic_hash_join(int kind, const TableView& probe, const TableView& b
   }
   gdf_error e = alloc_index_pair(capacity, &o_probe, &o_build);
   if (e != GDF_SUCCESS) return e;
+  B200_TIMED("join_generic_probe");
   if (left_like)
     probe_kernel<JOIN_LEFT, true><<<tiles, kThreads>>>(probe, build, table.as<unsigned long long>(), slots - 1,
                                                       o_probe, o_build, cursor);

@@ -32,6 +32,7 @@ constexpr unsigned kMaxParts = 256;
 constexpr size_t kRowsPerPartition = 1u << 20;  // target build rows per partition (table <= 32 MB)
 constexpr int kScatterRows = 16;                // rows per thread in the scatter tile
 constexpr int kScatterTile = kThreads * kScatterRows;
+constexpr int kBuildTile = kThreads * 8;
 constexpr int kProbeRows = 4;
 constexpr int kProbeTile = kThreads * kProbeRows;
 constexpr unsigned long long kEmptyKey = ~0ull;
@@ -62,51 +63,36 @@ struct PartGeom {
   __device__ __forceinline__ unsigned pid(uint32_t h) const { return nparts == 1 ? 0u : (h >> shift); }
 };
 
-// Rank one row per lane inside the warp's private histogram: no atomics, the lowest lane of every
-// group of equal pids bumps the counter for the whole group.  `pid` >= nparts means "row dropped".
-static __device__ __forceinline__ unsigned warp_rank(unsigned* __restrict__ whist, unsigned pid, bool keep) {
-  const unsigned kmask = __ballot_sync(0xffffffffu, keep);
-  unsigned rank = 0;
-  if (keep) {
-    const unsigned peers = __match_any_sync(kmask, pid);
-    const unsigned prior = whist[pid];
-    rank = prior + __popc(peers & lanemask_lt());
-    __syncwarp(kmask);
-    if ((int)lane_id() == __ffs(peers) - 1) whist[pid] = prior + __popc(peers);
-  }
-  __syncwarp();
-  return rank;
-}
-
-// ---- pass 1: per-partition row counts ----
+// ---- pass 1: per-partition row counts.  Shared-memory 32-bit atomics are the cheapest primitive on
+// B200 for this (~2900 Gop/s measured, profiles/r01_microbench.txt; match.any-based ranking measured
+// 20x slower), so the CTA histogram is plain atomicAdd on shared counters. ----
 template <typename KT, bool KEEP_NULLS>
 __global__ void __launch_bounds__(kThreads)
 part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
                  unsigned long long* __restrict__ totals) {
-  __shared__ unsigned whist[kThreads / 32][kMaxParts];
-  unsigned* mine = whist[threadIdx.x >> 5];
-  for (unsigned p = lane_id(); p < g.nparts; p += 32) mine[p] = 0;
-  __syncwarp();
+  __shared__ unsigned hist[kMaxParts];
+  for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) hist[p] = 0;
+  __syncthreads();
+  constexpr int U = 8;
   const size_t stride = (size_t)gridDim.x * kThreads;
-  const size_t n_round = (n + stride - 1) / stride * stride;
-  for (size_t r = (size_t)blockIdx.x * kThreads + threadIdx.x; r < n_round; r += stride) {
-    bool keep = r < n;
-    unsigned pid = 0;
-    if (keep) {
-      const bool ok = bit_valid(valid, r);
-      if (ok) pid = g.pid(KeyBits<KT>::hash(keys[r]));
-      else if (KEEP_NULLS) pid = (unsigned)r & (g.nparts - 1);
-      else keep = false;
+  for (size_t r0 = (size_t)blockIdx.x * kThreads + threadIdx.x; r0 < n; r0 += stride * U) {
+    KT k[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = r0 + (size_t)u * stride;
+      k[u] = r < n ? keys[r] : (KT)0;
     }
-    warp_rank(mine, pid, keep);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = r0 + (size_t)u * stride;
+      if (r >= n) continue;
+      if (bit_valid(valid, r)) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(k[u]))], 1u);
+      else if (KEEP_NULLS) atomicAdd(&hist[(unsigned)r & (g.nparts - 1)], 1u);
+    }
   }
   __syncthreads();
-  for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) {
-    unsigned s = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += whist[w][p];
-    if (s) atomicAdd(&totals[p], (unsigned long long)s);
-  }
+  for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads)
+    if (hist[p]) atomicAdd(&totals[p], (unsigned long long)hist[p]);
 }
 
 // ---- pass 2: write-combining scatter of {key,row} pairs ----
@@ -115,7 +101,7 @@ struct ScatterSmem {
   KT keys[kScatterTile];
   int32_t rows[kScatterTile];
   unsigned short pid[kScatterTile];
-  unsigned whist[kThreads / 32][kMaxParts];  // per-warp counts, then per-warp exclusive bases
+  unsigned hist[kMaxParts];                  // rows of this tile per partition
   unsigned lstart[kMaxParts];                // start of partition p inside the staged tile
   unsigned long long gbase[kMaxParts];       // reserved global start of this tile's run
   unsigned kept;
@@ -132,8 +118,8 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
   const size_t tiles = (n + kScatterTile - 1) / kScatterTile;
   for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const size_t base = tile * kScatterTile;
-    for (unsigned p = lane; p < g.nparts; p += 32) sm.whist[warp][p] = 0;
-    __syncwarp();
+    for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) sm.hist[p] = 0;
+    __syncthreads();
     KT k[kScatterRows];
     unsigned rp[kScatterRows];  // rank << 16 | pid, pid 0xffff = dropped, bit 15 = NULL-key row
     // a warp owns 32*kScatterRows consecutive rows; step i covers 32 consecutive rows (coalesced)
@@ -153,20 +139,13 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
         else if (KEEP_NULLS) { p = (unsigned)r & (g.nparts - 1); nullbit = 0x8000u; }
         else keep = false;
       }
-      const unsigned rank = warp_rank(sm.whist[warp], p, keep);
-      rp[i] = keep ? ((rank << 16) | p | nullbit) : 0xffffu;
+      rp[i] = keep ? ((atomicAdd(&sm.hist[p], 1u) << 16) | p | nullbit) : 0xffffu;
     }
     __syncthreads();
-    // per partition: exclusive scan over warps -> warp bases; total -> reserve global run
+    // per partition: reserve this tile's run in the global output with one atomic
     for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) {
-      unsigned run = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) {
-        const unsigned c = sm.whist[w][p];
-        sm.whist[w][p] = run;
-        run += c;
-      }
-      sm.lstart[p] = run;  // count for now
+      const unsigned run = sm.hist[p];
+      sm.lstart[p] = run;  // count for now, scanned below
       sm.gbase[p] = run ? atomicAdd(&cursors[p], (unsigned long long)run) : 0ull;
     }
     __syncthreads();
@@ -198,7 +177,7 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
     for (int i = 0; i < kScatterRows; ++i) {
       if ((rp[i] & 0xffffu) == 0xffffu) continue;
       const unsigned p = rp[i] & 0x7fffu;
-      const unsigned at = sm.lstart[p] + sm.whist[warp][p] + (rp[i] >> 16);
+      const unsigned at = sm.lstart[p] + (rp[i] >> 16);
       const int32_t r = (int32_t)(wbase + (size_t)i * 32 + lane);
       sm.keys[at] = k[i];
       sm.rows[at] = (rp[i] & 0x8000u) ? ~r : r;
@@ -235,8 +214,12 @@ struct Tables {
 template <typename KT>
 __global__ void __launch_bounds__(kThreads)
 part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[0]=dup [1]=sentinel key*/) {
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < b.n; i += stride) {
+  // One CTA = one contiguous tile of pairs, tiles dispatched in index order: the pairs are
+  // partition-contiguous, so the CTAs in flight insert into one or two partitions' tables at a time
+  // and those tables stay L2-resident (a grid-stride loop would touch every table at once).
+  const size_t tile_lo = (size_t)blockIdx.x * kBuildTile;
+  const size_t tile_hi = tile_lo + kBuildTile < b.n ? tile_lo + kBuildTile : b.n;
+  for (size_t i = tile_lo + threadIdx.x; i < tile_hi; i += kThreads) {
     int32_t row = b.rows ? b.rows[i] : (int32_t)i;
     if (!b.rows && !bit_valid(b.valid, i)) continue;
     const KT kraw = b.keys[i];
@@ -443,7 +426,10 @@ gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, S
   const size_t n = col->size;
   B200_CUDA_TRY(cudaMemsetAsync(d_totals, 0, g.nparts * sizeof(unsigned long long), 0));
   const int blocks = sm_count() * 4;
-  part_hist_kernel<KT, KEEP_NULLS><<<blocks, kThreads>>>(keys, col->valid, n, g, d_totals);
+  {
+    B200_TIMED("join_part_hist");
+    part_hist_kernel<KT, KEEP_NULLS><<<blocks, kThreads>>>(keys, col->valid, n, g, d_totals);
+  }
   B200_CHECK_LAST();
   B200_CUDA_TRY(cudaMemcpy(h_totals, d_totals, g.nparts * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   unsigned long long h_cursors[kMaxParts], run = 0;
@@ -460,8 +446,11 @@ gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, S
   const size_t tiles = (n + kScatterTile - 1) / kScatterTile;
   const size_t cap = (size_t)sm_count() * 3;
   const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
-  kern<<<sblocks, kThreads, sizeof(ScatterSmem<KT>)>>>(keys, col->valid, n, g, d_cursors, keys_out.as<KT>(),
-                                                      rows_out.as<int32_t>());
+  {
+    B200_TIMED("join_part_scatter");
+    kern<<<sblocks, kThreads, sizeof(ScatterSmem<KT>)>>>(keys, col->valid, n, g, d_cursors, keys_out.as<KT>(),
+                                                        rows_out.as<int32_t>());
+  }
   B200_CHECK_LAST();
   return GDF_SUCCESS;
 }
@@ -480,6 +469,7 @@ gdf_error launch_probe(bool unique, bool write, const Pairs<KT>& pr, PartGeom g,
                        int32_t* ob, unsigned long long* cursor) {
   const unsigned tiles = (unsigned)((pr.n + kProbeTile - 1) / kProbeTile);
   if (tiles == 0) return GDF_SUCCESS;
+  B200_TIMED(write ? "join_part_probe" : "join_part_count");
   if (unique) {
     if (write) part_probe_kernel<KT, LEFT_LIKE, true, true><<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
     else part_probe_kernel<KT, LEFT_LIKE, true, false><<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
@@ -551,10 +541,14 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   B200_CUDA_TRY(cudaMemcpy(d_tmask, h_tmask, g.nparts * sizeof(unsigned), cudaMemcpyHostToDevice));
   Scratch table;
   B200_CUDA_TRY(table.alloc(total_slots * sizeof(Slot)));
-  B200_CUDA_TRY(cudaMemsetAsync(table.ptr, 0xff, total_slots * sizeof(Slot), 0));
+  {
+    B200_TIMED("join_table_init");
+    B200_CUDA_TRY(cudaMemsetAsync(table.ptr, 0xff, total_slots * sizeof(Slot), 0));
+  }
   Tables t{table.as<Slot>(), d_toffset, d_tmask};
   if (bp.n) {
-    part_build_kernel<KT><<<grid_for(bp.n), kThreads>>>(bp, g, t, d_flags);
+    B200_TIMED("join_part_build");
+    part_build_kernel<KT><<<(unsigned)((bp.n + kBuildTile - 1) / kBuildTile), kThreads>>>(bp, g, t, d_flags);
     B200_CHECK_LAST();
   }
   int h_flags[2] = {0, 0};

@@ -185,6 +185,7 @@ gdf_error launch_reduce(gdf_column* col, T identity, T* dev_result, gdf_size_typ
   if (need < 1) need = 1;
   if ((size_t)blocks > need) blocks = (int)need;
   T* partials = static_cast<T*>(s->partials);
+  B200_TIMED("reduce");
   if (aligned16(data))
     reduce_kernel<T, Op, SQUARE, true><<<blocks, kThreads>>>(data, col->valid, n, identity, partials, s->ticket, dev_result);
   else

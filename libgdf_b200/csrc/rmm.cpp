@@ -4,11 +4,12 @@
 // The reference sub-allocates one big cudaMalloc with the vendored cnmem pool.  On CUDA 12 the
 // driver's stream-ordered allocator does that job natively, so:
 //   * CudaDefaultAllocation  -> cudaMalloc / cudaFree (same as the reference's default mode)
-//   * PoolAllocation         -> cudaMallocAsync / cudaFreeAsync on the device's default mempool whose
-//                               release threshold is raised to "never give memory back"; an
-//                               initial_pool_size > 0 pre-warms the pool with one alloc+free.
-// Both kinds of pointer may be released through either path (the CUDA runtime allows cudaFree on
-// async allocations and vice versa), so changing mode between alloc and free is safe.
+//   * PoolAllocation         -> a caching allocator (block_cache.h): freed blocks are kept and handed
+//                               back for the next request of about the same size, so warm operator
+//                               calls never enter the driver - the property cnmem gives the
+//                               reference.  An initial_pool_size > 0 pre-warms one block of that size.
+// A pointer from either mode may be released in either mode (rmmFree falls back to cudaFree for
+// pointers the cache does not own), so changing mode between alloc and free is safe.
 // The optional event log keeps the reference's CSV schema (memory_manager.cpp:46-64).
 #include <cuda_runtime_api.h>
 
@@ -21,6 +22,8 @@
 #include <vector>
 
 #include <rmm.h>
+
+#include "block_cache.h"
 
 namespace {
 
@@ -42,7 +45,6 @@ struct Manager {
   std::vector<Event> events;
   std::set<void*> live;
   Clock::time_point base = Clock::now();
-  std::set<int> tuned_devices;
 };
 
 Manager& mgr() {
@@ -61,22 +63,9 @@ rmmError_t from_cuda(cudaError_t e) {
   return RMM_ERROR_CUDA_ERROR;
 }
 
-// Raise the release threshold of the current device's default pool once.
-cudaError_t tune_pool_for_current_device() {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  Manager& m = mgr();
-  std::lock_guard<std::mutex> g(m.mu);
-  if (m.tuned_devices.count(dev)) return cudaSuccess;
-  cudaMemPool_t pool;
-  e = cudaDeviceGetDefaultMemPool(&pool, dev);
-  if (e != cudaSuccess) return e;
-  uint64_t never = UINT64_MAX;
-  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
-  if (e != cudaSuccess) return e;
-  m.tuned_devices.insert(dev);
-  return cudaSuccess;
+b200::BlockCache& pool() {
+  static b200::BlockCache* c = new b200::BlockCache();  // leaked on purpose (exit-order safety)
+  return *c;
 }
 
 struct LogScope {
@@ -138,15 +127,12 @@ rmmError_t rmmInitialize(rmmOptions_t* options) {
     mgr().opts = *options;
   }
   if (pool_mode()) {
-    cudaError_t e = tune_pool_for_current_device();
-    if (e != cudaSuccess) return from_cuda(e);
     size_t warm = mgr().opts.initial_pool_size;
-    if (warm) {  // reserve the requested pool up front, then hand it back to the (non-releasing) pool
+    if (warm) {  // reserve the requested amount up front and park it in the cache
       void* p = nullptr;
-      e = cudaMallocAsync(&p, warm, 0);
+      cudaError_t e = pool().alloc(&p, warm);
       if (e != cudaSuccess) return from_cuda(e);
-      e = cudaFreeAsync(p, 0);
-      if (e != cudaSuccess) return from_cuda(e);
+      pool().release(p);
     }
   }
   return RMM_SUCCESS;
@@ -155,14 +141,7 @@ rmmError_t rmmInitialize(rmmOptions_t* options) {
 rmmError_t rmmFinalize() {
   Manager& m = mgr();
   std::lock_guard<std::mutex> g(m.mu);
-  if (m.opts.allocation_mode == PoolAllocation) {
-    // give cached blocks back to the driver; ignore failure at process teardown
-    for (int dev : m.tuned_devices) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    }
-    cudaGetLastError();
-  }
+  pool().trim();  // give cached blocks back to the driver
   m.events.clear();
   m.live.clear();
   m.opts = rmmOptions_t{CudaDefaultAllocation, 0, false};
@@ -173,13 +152,7 @@ rmmError_t rmmAlloc(void** ptr, size_t size, cudaStream_t stream) {
   if (!ptr && !size) return RMM_SUCCESS;
   if (!ptr) return RMM_ERROR_INVALID_ARGUMENT;
   LogScope log(0, nullptr, size, stream);
-  cudaError_t e;
-  if (pool_mode()) {
-    e = tune_pool_for_current_device();
-    if (e == cudaSuccess) e = cudaMallocAsync(ptr, size, stream);
-  } else {
-    e = cudaMalloc(ptr, size);
-  }
+  const cudaError_t e = pool_mode() ? pool().alloc(ptr, size) : cudaMalloc(ptr, size);
   if (e != cudaSuccess) return from_cuda(e);
   log.ptr = *ptr;
   return RMM_SUCCESS;
@@ -188,8 +161,8 @@ rmmError_t rmmAlloc(void** ptr, size_t size, cudaStream_t stream) {
 rmmError_t rmmFree(void* ptr, cudaStream_t stream) {
   LogScope log(2, ptr, 0, stream);
   if (!ptr) return RMM_SUCCESS;  // cudaFree(nullptr) is a no-op in the reference as well
-  cudaError_t e = pool_mode() ? cudaFreeAsync(ptr, stream) : cudaFree(ptr);
-  return from_cuda(e);
+  if (pool().release(ptr)) return RMM_SUCCESS;  // block came from the cache (whatever the mode is now)
+  return from_cuda(cudaFree(ptr));
 }
 
 // Same contract as the reference (memory.cpp:172-194): the old block is released, contents are
@@ -199,11 +172,10 @@ rmmError_t rmmRealloc(void** ptr, size_t new_size, cudaStream_t stream) {
   if (!ptr) return RMM_ERROR_INVALID_ARGUMENT;
   LogScope log(1, nullptr, new_size, stream);
   rmmError_t r = RMM_SUCCESS;
-  if (*ptr) {
-    cudaError_t e = pool_mode() ? cudaFreeAsync(*ptr, stream) : cudaFree(*ptr);
-    if ((r = from_cuda(e)) != RMM_SUCCESS) return r;
+  if (*ptr && !pool().release(*ptr)) {
+    if ((r = from_cuda(cudaFree(*ptr))) != RMM_SUCCESS) return r;
   }
-  cudaError_t e = pool_mode() ? cudaMallocAsync(ptr, new_size, stream) : cudaMalloc(ptr, new_size);
+  const cudaError_t e = pool_mode() ? pool().alloc(ptr, new_size) : cudaMalloc(ptr, new_size);
   if ((r = from_cuda(e)) != RMM_SUCCESS) return r;
   log.ptr = *ptr;
   return RMM_SUCCESS;

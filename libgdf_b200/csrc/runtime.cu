@@ -2,10 +2,16 @@
 // NVTX ranges, plus the library-internal scratch allocator.  Reference behaviour followed:
 //   libgdf/src/column.cpp:160-275, src/context.cpp:3-11, src/errorhandling.cpp:5-35,
 //   src/cudautils.cu:4-14, src/nvtx_utils.cpp:19-71.
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
 
 #include <nvtx3/nvToolsExt.h>
 
+#include "block_cache.h"
 #include "common.cuh"
 
 namespace b200 {
@@ -22,31 +28,14 @@ int sm_count() {
   return cached[dev];
 }
 
-static cudaError_t tune_default_pool() {
-  static std::mutex mu;
-  static bool tuned[64] = {false};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  std::lock_guard<std::mutex> g(mu);
-  if (dev >= 0 && dev < 64 && !tuned[dev]) {
-    cudaMemPool_t pool;
-    e = cudaDeviceGetDefaultMemPool(&pool, dev);
-    if (e != cudaSuccess) return e;
-    uint64_t never = UINT64_MAX;
-    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
-    if (e != cudaSuccess) return e;
-    tuned[dev] = true;
-  }
-  return cudaSuccess;
+static BlockCache& scratch_cache() {
+  static BlockCache* c = new BlockCache();  // leaked on purpose: no teardown-order issues at exit
+  return *c;
 }
-
-cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
-  cudaError_t e = tune_default_pool();
-  if (e != cudaSuccess) return e;
-  return cudaMallocAsync(p, bytes, s);
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t /*s*/) { return scratch_cache().alloc(p, bytes); }
+cudaError_t scratch_free(void* p, cudaStream_t /*s*/) {
+  return scratch_cache().release(p) ? cudaSuccess : cudaFree(p);
 }
-cudaError_t scratch_free(void* p, cudaStream_t s) { return cudaFreeAsync(p, s); }
 
 void* pinned_mailbox() {
   static thread_local void* box = nullptr;
@@ -56,7 +45,96 @@ void* pinned_mailbox() {
   return box;
 }
 
+// ---- per-kernel timing ----
+namespace {
+struct Pending {
+  const char* name;
+  cudaEvent_t start, stop;
+};
+struct Profiler {
+  std::mutex mu;
+  bool enabled = false;
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  std::map<std::string, std::pair<long long, double>> totals;  // name -> {launches, ms}
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+Profiler& prof() {
+  static Profiler p;
+  return p;
+}
+}  // namespace
+
+KernelTimer::KernelTimer(const char* name) : slot(-1) {
+  Profiler& p = prof();
+  if (!p.enabled) return;
+  std::lock_guard<std::mutex> g(p.mu);
+  Pending pe{name, p.get(), p.get()};
+  if (!pe.start || !pe.stop) return;
+  cudaEventRecord(pe.start, 0);
+  slot = (int)p.pending.size();
+  p.pending.push_back(pe);
+}
+KernelTimer::~KernelTimer() {
+  if (slot < 0) return;
+  Profiler& p = prof();
+  std::lock_guard<std::mutex> g(p.mu);
+  if (slot < (int)p.pending.size()) cudaEventRecord(p.pending[slot].stop, 0);
+}
+
 }  // namespace b200
+
+extern "C" int gdfx_profile_enable(int on) {
+  b200::Profiler& p = b200::prof();
+  std::lock_guard<std::mutex> g(p.mu);
+  const int was = p.enabled;
+  p.enabled = on != 0;
+  return was;
+}
+
+extern "C" size_t gdfx_profile_report(char* buf, size_t capacity) {
+  b200::Profiler& p = b200::prof();
+  std::lock_guard<std::mutex> g(p.mu);
+  cudaDeviceSynchronize();
+  for (const b200::Pending& pe : p.pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.start, pe.stop) == cudaSuccess) {
+      auto& t = p.totals[pe.name];
+      t.first += 1;
+      t.second += ms;
+    }
+    p.pool.push_back(pe.start);
+    p.pool.push_back(pe.stop);
+  }
+  cudaGetLastError();
+  p.pending.clear();
+  std::string out = "{";
+  bool first = true;
+  for (const auto& kv : p.totals) {
+    char line[256];
+    snprintf(line, sizeof line, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+             kv.second.first, kv.second.second);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  p.totals.clear();
+  if (buf && capacity) {
+    const size_t n = out.size() < capacity - 1 ? out.size() : capacity - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return out.size() + 1;
+}
 
 extern "C" {
 

@@ -7,7 +7,7 @@ from .._cdef import header_cdef
 from .wrapper import GDFError, _libgdf_wrapper
 
 ffi = cffi.FFI()
-ffi.cdef(header_cdef("gdf/cffi/types.h", "gdf/cffi/functions.h"))
+ffi.cdef(header_cdef("gdf/cffi/types.h", "gdf/cffi/functions.h", "gdf_b200_ext.h"))
 
 # librmm.so is found through libgdf.so's $ORIGIN rpath.
 libgdf_api = ffi.dlopen(lib_path("libgdf.so"))
