@@ -9,3 +9,8 @@
  * measure the dominant kernel's launch duration live, inside the timed region. */
 int gdfx_profile_enable(int on);
 size_t gdfx_profile_report(char *buf, size_t capacity);
+
+/* Multi-GPU layer helper (libgdf_b200/dist.py): indices[i] = payload[indices[i]] in place for every
+ * non-negative entry (< payload_rows), -1 otherwise.  `indices` is a GDF_INT32 join output column;
+ * `payload` is a device array of the global row ids that travelled with the exchanged keys. */
+gdf_error gdfx_remap_indices(gdf_column *indices, const int32_t *payload, size_t payload_rows);

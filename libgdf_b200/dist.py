@@ -1,0 +1,207 @@
+"""Multi-GPU layer: hash joins and hash group-bys sharded over the ranks of one torch.distributed
+process group (one process per GPU, NCCL over NVLink 5 / NVSwitch).
+
+The reference has no multi-device code at all (no NCCL/MPI call site, the join
+even hard-codes ``prefetch(0)``, ref src/join/hash/join_compute_api.h:397).  Its only partitioner is the
+single-GPU ``gdf_hash_partition`` (ref src/hashing.cu:559-654); this module is the layer one would put
+on top of it, built from the same C-ABI operators:
+
+    join      rows are block-distributed.  Every rank radix-partitions its local (key, global row id)
+              rows into G = world_size hash partitions with ``gdf_hash_partition`` (destination =
+              murmur3(key) & (G-1) / % G), exchanges the partition sizes and then the partitions
+              themselves with ONE ``all_to_all_single`` per column, joins what it received with the
+              single-GPU ``gdf_inner_join`` / ``gdf_left_join`` and maps the local result indices back
+              to global row ids.  Equal keys always meet on one rank; output stays sharded.
+    group-by  two-phase: local ``gdf_group_by_sum`` first (at most #groups partial rows per rank,
+              which also removes Zipf skew: a hot key becomes ONE partial row per rank), then the
+              partials are hash-partitioned, exchanged and merged with a second ``gdf_group_by_sum``.
+    filter / reductions / binary ops   embarrassingly parallel: callers run the single-GPU operator per
+              shard (global row index = local index + shard offset); nothing to exchange.
+
+The exchange plan (``exchange``) is backend-agnostic torch.distributed code and is unit-tested on CPU
+with the gloo backend and world_size 2 (tests/test_dist_cpu.py), where the per-shard operators are
+injected by the test.  The product operators (``GdfOps``) are the CUDA C ABI and nothing else: there
+is no CPU fallback in this module.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------------------------
+# per-shard operators: the gdf_* C ABI on CUDA tensors
+# ------------------------------------------------------------------------------------------------
+class GdfOps(object):
+    """Single-GPU operators used by the distributed algorithms, all through libgdf.so."""
+
+    def __init__(self):
+        from . import columns as C
+        from .libgdf_cffi import ffi, libgdf
+        self.C, self.ffi, self.lib = C, ffi, libgdf
+        self.ctx = ffi.new("gdf_context*")
+        libgdf.gdf_context_view(self.ctx, 0, libgdf.GDF_HASH, 0, 0, 0)
+
+    def hash_partition(self, cols, nparts):
+        """cols[0] is the key.  Returns (partition-contiguous columns, start offset of each partition)."""
+        C, ffi, lib = self.C, self.ffi, self.lib
+        n = cols[0].numel()
+        if n == 0:
+            return [c.clone() for c in cols], [0] * nparts
+        ins = [C.Column(c) for c in cols]
+        outs = [C.Column(torch.empty_like(c)) for c in cols]
+        offsets = ffi.new("int[]", nparts)
+        lib.gdf_hash_partition(len(ins), C.column_array(ins), ffi.new("int[]", [0]), 1, nparts, C.column_array(outs),
+                               offsets, lib.GDF_HASH_MURMUR3)
+        return [o.data for o in outs], list(offsets)
+
+    def _join(self, fn, lkeys, rkeys, lpayload, rpayload):
+        C, ffi, lib = self.C, self.ffi, self.lib
+        L, R = C.Column(lkeys), C.Column(rkeys)
+        out_l, out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
+        idx = ffi.new("int[]", [0])
+        fn(C.column_array([L]), 1, idx, C.column_array([R]), 1, idx, 1, 0, ffi.NULL, out_l, out_r, self.ctx)
+        # local result indices -> global row ids, in place on the library-owned buffers
+        if int(out_l.size):
+            lib.gdfx_remap_indices(out_l, ffi.cast("int32_t*", lpayload.data_ptr()), lpayload.numel())
+            lib.gdfx_remap_indices(out_r, ffi.cast("int32_t*", rpayload.data_ptr()), rpayload.numel())
+        return C.library_owned_to_torch(out_l), C.library_owned_to_torch(out_r)
+
+    def inner_join(self, lkeys, rkeys, lpayload, rpayload):
+        return self._join(self.lib.gdf_inner_join, lkeys, rkeys, lpayload, rpayload)
+
+    def left_join(self, lkeys, rkeys, lpayload, rpayload):
+        return self._join(self.lib.gdf_left_join, lkeys, rkeys, lpayload, rpayload)
+
+    def group_by_sum(self, keys, vals):
+        C, ffi, lib = self.C, self.ffi, self.lib
+        n = keys.numel()
+        if n == 0:
+            return keys.clone(), vals.clone()
+        K, V = C.Column(keys), C.Column(vals)
+        OK, OV = C.Column(torch.empty_like(keys)), C.Column(torch.empty_like(vals))
+        lib.gdf_group_by_sum(1, C.column_array([K]), V.cdata, ffi.NULL, C.column_array([OK]), OV.cdata, self.ctx)
+        g = int(OV.cdata.size)
+        return OK.data[:g], OV.data[:g]
+
+
+# ------------------------------------------------------------------------------------------------
+# the exchange step (backend-agnostic: nccl on GPUs, gloo in the CPU unit tests)
+# ------------------------------------------------------------------------------------------------
+def exchange(cols, offsets, group=None):
+    """Personalised all-to-all of partition-contiguous columns.
+
+    cols     list of 1-D tensors, all with n rows, partition p occupying rows [offsets[p], offsets[p+1])
+    offsets  world_size start offsets (the host ``partition_offsets`` array of gdf_hash_partition)
+    Returns (received columns, recv_counts): the rows every rank sent to this one, source-rank major.
+    One int64 counts exchange + ONE all_to_all_single per column.
+    """
+    world = dist.get_world_size(group)
+    n = cols[0].numel()
+    bounds = list(offsets) + [n]
+    send_counts = [int(bounds[p + 1] - bounds[p]) for p in range(world)]
+    dev = cols[0].device
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    rc = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.tolist()]
+    total = sum(recv_counts)
+    outs = []
+    for c in cols:
+        out = torch.empty(total, dtype=c.dtype, device=dev)
+        dist.all_to_all_single(out, c.contiguous(), recv_counts, send_counts, group=group)
+        outs.append(out)
+    return outs, recv_counts
+
+
+def shard_bounds(total_rows, world, rank):
+    """Block distribution of total_rows over world ranks: [lo, hi) of `rank`."""
+    per = (total_rows + world - 1) // world
+    lo = min(total_rows, rank * per)
+    return lo, min(total_rows, lo + per)
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed operators
+# ------------------------------------------------------------------------------------------------
+def _global_ids(n, offset, device):
+    if offset + n >= 2 ** 31:
+        raise ValueError("global row ids must fit int32 (gdf join indices are GDF_INT32)")
+    return torch.arange(offset, offset + n, dtype=torch.int32, device=device)
+
+
+def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops, group=None, timings=None):
+    """Hash join of block-distributed key columns.
+
+    left_keys / right_keys   this rank's shard of the (single, integer) key column
+    left_offset/right_offset global row index of the shard's first row
+    Returns (left_idx, right_idx): int32 GLOBAL row ids of this rank's share of the result (-1 =
+    no partner, LEFT join).  The union over ranks is the join of the full tables (pair order
+    unspecified, as in the reference).
+    """
+    world = dist.get_world_size(group)
+    dev = left_keys.device
+    ev = _Stamps(timings, dev)
+    lids = _global_ids(left_keys.numel(), left_offset, dev)
+    rids = _global_ids(right_keys.numel(), right_offset, dev)
+    if world == 1:
+        fn = ops.inner_join if kind == "inner" else ops.left_join
+        out = fn(left_keys, right_keys, lids, rids)
+        ev.mark("local_join")
+        return out
+    (lk, li), loff = ops.hash_partition([left_keys, lids], world)
+    (rk, ri), roff = ops.hash_partition([right_keys, rids], world)
+    ev.mark("partition")
+    (lk, li), _ = exchange([lk, li], loff, group)
+    (rk, ri), _ = exchange([rk, ri], roff, group)
+    ev.mark("all_to_all")
+    fn = ops.inner_join if kind == "inner" else ops.left_join
+    out = fn(lk, rk, li, ri)
+    ev.mark("local_join")
+    return out
+
+
+def distributed_group_by_sum(keys, vals, ops, group=None, timings=None):
+    """Two-phase hash group-by SUM of block-distributed (key, value) rows.  Returns this rank's share
+    of the groups: every distinct key appears on exactly one rank."""
+    world = dist.get_world_size(group)
+    ev = _Stamps(timings, keys.device)
+    pk, pv = ops.group_by_sum(keys, vals)          # phase 1: local partials (<= #groups rows)
+    ev.mark("local_groupby")
+    if world == 1:
+        return pk, pv
+    (pk, pv), off = ops.hash_partition([pk, pv], world)
+    ev.mark("partition")
+    (pk, pv), _ = exchange([pk, pv], off, group)
+    ev.mark("all_to_all")
+    out = ops.group_by_sum(pk, pv)                 # phase 2: merge the partials this rank owns
+    ev.mark("merge")
+    return out
+
+
+class _Stamps(object):
+    """Optional per-phase device timing (CUDA events on the current stream)."""
+
+    def __init__(self, sink, device):
+        self.sink = sink
+        self.cuda = sink is not None and device.type == "cuda"
+        self.last = self._now() if self.cuda else None
+
+    def _now(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def mark(self, name):
+        if not self.cuda:
+            return
+        e = self._now()
+        self.sink.setdefault("_events", []).append((name, self.last, e))
+        self.last = e
+
+
+def resolve_timings(sink):
+    """After a synchronize: fold recorded event pairs into {phase: ms}."""
+    out = {}
+    for name, a, b in sink.pop("_events", []):
+        out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+    return out
