@@ -54,7 +54,7 @@ __host__ __device__ inline int dtype_width(int dtype) {
 
 inline size_t valid_bytes(size_t rows) { return (rows + 7) / 8; }  // ref include/gdf/utils.h:21-23
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ----------------------------------------------------------------------------------------------
 // Stream-ordered scratch.  Library-internal temporaries (hash tables, partition buffers, look-back

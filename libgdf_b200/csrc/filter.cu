@@ -18,6 +18,7 @@
 //   apply_stencil       streamcompactionops.cu:208-339   see DESIGN.md "quirks" for the two
 //                       documented divergences (LESS_THAN operators, rebuilt output mask).
 #include "select.cuh"
+#include "select_stream.cuh"
 
 namespace b200 {
 namespace {
@@ -149,6 +150,54 @@ struct StencilPolicy {
   }
   __device__ void emit(size_t row, size_t pos) const { out[pos] = data[row]; }
 };
+
+// gdf_filter, one 16-byte aligned column: streaming kernel (select_stream.cuh)
+template <typename T>
+struct EqualsDeviceScalar {  // row kept when !(value != *d_vals[0])  (ref sqls_rtti_comp.hpp:200-213)
+  const void* const* d_vals;
+  T target;
+  __device__ void prepare() { target = *static_cast<const T*>(d_vals[0]); }
+  __device__ bool operator()(T v) const { return !(v != target); }
+};
+struct EmitRowIndex {
+  size_t* out;
+  __device__ void operator()(size_t row, size_t pos) const { out[pos] = row; }
+};
+
+gdf_error read_count(const unsigned long long* d_count, size_t* h_count) {
+  unsigned long long* box = static_cast<unsigned long long*>(pinned_mailbox());
+  B200_REQUIRE(box != nullptr, GDF_CUDA_ERROR);
+  B200_CUDA_TRY(cudaMemcpyAsync(box, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, 0));
+  B200_CUDA_TRY(cudaStreamSynchronize(0));
+  *h_count = (size_t)*box;
+  return GDF_SUCCESS;
+}
+
+template <typename T>
+gdf_error run_filter_stream(const T* data, size_t n, const void* const* d_vals, size_t* out, size_t* h_count) {
+  using G = select_stream::Geom<T>;
+  const size_t tiles = (n + G::kTileRows - 1) / G::kTileRows;
+  B200_REQUIRE(tiles < (1ull << 31), GDF_COLUMN_SIZE_TOO_BIG);
+  Scratch desc;  // [tiles] look-back descriptors | selected count | ticket counter
+  const size_t bytes = tiles * sizeof(uint64_t) + 2 * sizeof(unsigned long long);
+  B200_CUDA_TRY(desc.alloc(bytes));
+  B200_CUDA_TRY(cudaMemsetAsync(desc.ptr, 0, bytes, 0));
+  uint64_t* d = desc.as<uint64_t>();
+  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + tiles);
+  unsigned* ticket = reinterpret_cast<unsigned*>(d_count + 1);
+  auto kern = select_stream::select_stream_kernel<T, EqualsDeviceScalar<T>, EmitRowIndex>;
+  const int smem = (int)select_stream::smem_bytes<T>();
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const size_t resident = (size_t)sm_count() * 2;  // 2 CTAs x ~97 KB of shared memory per SM
+  const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
+  {
+    B200_TIMED("select");
+    kern<<<blocks, select_stream::kThreads, smem>>>(data, n, EqualsDeviceScalar<T>{d_vals, T()}, EmitRowIndex{out}, d,
+                                                    ticket, d_count);
+  }
+  B200_CHECK_LAST();
+  return read_count(d_count, h_count);
+}
 
 // Launch one select pass; returns the number of selected rows through *h_count (host).
 template <typename Policy>
@@ -403,6 +452,8 @@ extern "C" gdf_error gdf_filter(size_t nrows, gdf_column* cols, size_t ncols, vo
   if (ncols == 1) {
 #define B200_FILTER_ONE(T)                                   \
   {                                                          \
+    if (nrows && aligned16(cols[0].data))                    \
+      return run_filter_stream<T>(static_cast<const T*>(cols[0].data), nrows, d_vals, d_indx, new_sz); \
     FilterOne<T> pol;                                        \
     pol.data = static_cast<const T*>(cols[0].data);          \
     pol.d_vals = d_vals;                                     \

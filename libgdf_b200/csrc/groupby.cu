@@ -219,38 +219,6 @@ __global__ void init_fast_kernel(FastSlot* tab, unsigned long long* cnt, size_t 
   }
 }
 
-template <typename KT> __device__ __forceinline__ uint32_t hash_key(unsigned long long bits) {
-  return murmur3_32<sizeof(KT)>(bits);
-}
-
-// Fold (v, c) for `key` into the global table.  Returns false if no slot was found within the probe
-// bound (table too small for the number of groups).
-static __device__ __forceinline__ bool global_fold(FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt,
-                                                   unsigned mask, unsigned slots, unsigned probe_limit,
-                                                   unsigned long long key, uint32_t h, int64_t v,
-                                                   unsigned long long c, int fold_op, int* side_used) {
-  if (key == kEmptyKey) {  // a real key equal to the EMPTY pattern lives in the side slot
-    fold(&tab[slots].acc, v, fold_op);
-    if (cnt) atomicAdd(&cnt[slots], c);
-    *side_used = 1;
-    return true;
-  }
-  unsigned s = h & mask;
-  for (unsigned probe = 0; probe < probe_limit; ++probe, s = (s + 1) & mask) {
-    unsigned long long k = tab[s].key;  // plain load: a stale EMPTY only costs a failed CAS
-    if (k == kEmptyKey) {
-      const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
-      k = (prev == kEmptyKey) ? key : prev;
-    }
-    if (k == key) {
-      fold(&tab[s].acc, v, fold_op);
-      if (cnt) atomicAdd(&cnt[s], c);
-      return true;
-    }
-  }
-  return false;
-}
-
 // 64-bit wrapping add in SHARED memory built from 32-bit atomics: on B200 a 32-bit shared atomic
 // runs ~8x faster than a 64-bit one (profiles/r01_microbench.txt: ~2900 vs ~400 Gop/s), and for
 // small non-negative addends the high word is touched only on a carry.
@@ -262,92 +230,7 @@ static __device__ __forceinline__ void smem_add64(unsigned long long* acc, int64
   if (up) atomicAdd(&w[1], up);
 }
 
-constexpr int kFastThreads = 1024;       // one CTA per SM, the CTA owns the SM's shared memory
-constexpr unsigned kCacheSlots = 8192;   // per-CTA hot-key cache: 8192 x {key 8 B, acc 8 B, cnt 4 B}
-constexpr unsigned kCacheProbes = 4;
-
-struct FastCache {
-  unsigned long long key[kCacheSlots];
-  unsigned long long acc[kCacheSlots];
-  unsigned cnt[kCacheSlots];
-};
-
-// Per-CTA shared-memory aggregation in front of the L2-resident global table.  Every row first tries
-// the CTA's cache (first-come, bounded linear probing); only rows whose key did not get a cache
-// slot go to the global table.  Under a Zipf key distribution the hot keys claim their slots within
-// the first few thousand rows of a CTA and are then folded with shared-memory atomics only - the
-// single hottest key of C4 (9.5 % of all rows) would otherwise serialise ~1e8 same-address L2 atomics.
-// The cache is flushed into the global table once, when the CTA has consumed its share of the rows.
-template <typename KT, typename IT>
-__global__ void __launch_bounds__(kFastThreads, 1)
-build_fast_kernel(const KT* __restrict__ key_col, const IT* __restrict__ values, size_t n, int op,
-                  FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt, unsigned mask, unsigned slots,
-                  unsigned probe_limit, int* __restrict__ flags /*[0]=side slot used, [1]=overflow*/) {
-  using UK = typename std::conditional<sizeof(KT) == 8, unsigned long long, unsigned>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FastCache& cache = *reinterpret_cast<FastCache*>(smem_raw);
-  const int fold_op = (op == OP_COUNT || op == OP_AVG) ? OP_SUM : op;
-  const bool additive = fold_op == OP_SUM;
-  const int64_t identity = op == OP_MIN ? (int64_t)std::numeric_limits<IT>::max()
-                                        : (op == OP_MAX ? (int64_t)std::numeric_limits<IT>::lowest() : 0);
-  for (unsigned i = threadIdx.x; i < kCacheSlots; i += kFastThreads) {
-    cache.key[i] = kEmptyKey;
-    cache.acc[i] = (unsigned long long)identity;
-    cache.cnt[i] = 0;
-  }
-  __syncthreads();
-  // contiguous share of rows per CTA, walked with a CTA-wide stride so loads stay coalesced
-  const size_t per = (n + gridDim.x - 1) / gridDim.x;
-  const size_t lo = (size_t)blockIdx.x * per;
-  const size_t hi = lo + per < n ? lo + per : n;
-  constexpr int U = 4;
-  for (size_t base = lo; base < hi; base += (size_t)kFastThreads * U) {
-    unsigned long long k[U];
-    int64_t v[U];
-    bool live[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t r = base + (size_t)u * kFastThreads + threadIdx.x;
-      live[u] = r < hi;
-      k[u] = live[u] ? (unsigned long long)(UK)key_col[r] : 0ull;
-      v[u] = (live[u] && op != OP_COUNT) ? (int64_t)values[r] : 1;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!live[u]) continue;
-      const uint32_t h = hash_key<KT>(k[u]);
-      bool done = false;
-      if (k[u] != kEmptyKey) {
-        unsigned s = (h >> 7) & (kCacheSlots - 1);  // bits disjoint from the global slot's low bits
-#pragma unroll
-        for (unsigned p = 0; p < kCacheProbes && !done; ++p, s = (s + 1) & (kCacheSlots - 1)) {
-          unsigned long long ck = cache.key[s];
-          if (ck == kEmptyKey) {
-            const unsigned long long prev = atomicCAS(&cache.key[s], kEmptyKey, k[u]);
-            ck = (prev == kEmptyKey) ? k[u] : prev;
-          }
-          if (ck == k[u]) {
-            if (additive) smem_add64(&cache.acc[s], v[u]);
-            else if (fold_op == OP_MIN) atomicMin(reinterpret_cast<long long*>(&cache.acc[s]), (long long)v[u]);
-            else atomicMax(reinterpret_cast<long long*>(&cache.acc[s]), (long long)v[u]);
-            if (cnt) atomicAdd(&cache.cnt[s], 1u);
-            done = true;
-          }
-        }
-      }
-      if (!done && !global_fold(tab, cnt, mask, slots, probe_limit, k[u], h, v[u], 1ull, fold_op, &flags[0]))
-        flags[1] = 1;
-    }
-  }
-  __syncthreads();
-  for (unsigned i = threadIdx.x; i < kCacheSlots; i += kFastThreads) {
-    const unsigned long long ck = cache.key[i];
-    if (ck == kEmptyKey) continue;
-    if (!global_fold(tab, cnt, mask, slots, probe_limit, ck, hash_key<KT>(ck), (int64_t)cache.acc[i],
-                     (unsigned long long)cache.cnt[i], fold_op, &flags[0]))
-      flags[1] = 1;
-  }
-}
+#include "groupby_fast.cuh"
 
 template <typename KT, typename IT, typename OT>
 __global__ void __launch_bounds__(kThreads)
@@ -462,8 +345,6 @@ gdf_error groupby_generic(const TableView& keys, const KeyOut& ko, const void* v
   return GDF_SUCCESS;
 }
 
-#include "groupby_fast.cuh"
-
 // ---- fast driver: one bounded, L2-resident table.  If the keys do not fit (more groups than the
 // table can hold within the probe bound) the call reports `overflowed` and the caller reruns the
 // input through the generic two-level path. ----
@@ -492,17 +373,26 @@ gdf_error groupby_fast(const KT* key_col, size_t n, const void* values, int op, 
                                                                (size_t)slots + 1, identity);
   }
   B200_CHECK_LAST();
-  auto kern = build_fast_kernel_v3<KT, VT>;
-  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastCache3)));
-  size_t want = (n + kGrabRows - 1) / kGrabRows;                 // one warp-grab each
-  want = (want + kFastThreads3 / 32 - 1) / (kFastThreads3 / 32);  // CTAs needed
-  const size_t resident = (size_t)sm_count() * 2;
+  const int fold_op = (op == OP_MIN) ? OP_MIN : (op == OP_MAX ? OP_MAX : OP_SUM);
+  const bool count_rows = op == OP_COUNT, with_cnt = op == OP_AVG;
+  void (*kern)(const KT*, const VT*, size_t, FastSlot*, unsigned long long*, unsigned, unsigned, unsigned, int*,
+               unsigned long long*) = nullptr;
+  if (count_rows) kern = build_fast_kernel_v4<KT, VT, OP_SUM, true, false>;
+  else if (with_cnt) kern = build_fast_kernel_v4<KT, VT, OP_SUM, false, true>;
+  else if (fold_op == OP_MIN) kern = build_fast_kernel_v4<KT, VT, OP_MIN, false, false>;
+  else if (fold_op == OP_MAX) kern = build_fast_kernel_v4<KT, VT, OP_MAX, false, false>;
+  else kern = build_fast_kernel_v4<KT, VT, OP_SUM, false, false>;
+  const int smem = (int)(sizeof(FastCache4) + (with_cnt ? kCacheSlots4 * sizeof(unsigned) : 0));
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  size_t want = (n + kGrabRows4 - 1) / kGrabRows4;                 // one warp-grab each
+  want = (want + kFastThreads4 / 32 - 1) / (kFastThreads4 / 32);    // CTAs needed
+  const size_t resident = (size_t)sm_count();                      // one 1024-thread CTA per SM
   const int blocks = (int)(want < resident ? (want ? want : 1) : resident);
   {
     B200_TIMED("groupby_build_fast");
-    kern<<<blocks, kFastThreads3, sizeof(FastCache3)>>>(key_col, static_cast<const VT*>(values), n, op,
-                                                       tab.as<FastSlot>(), cnt.as<unsigned long long>(), slots - 1,
-                                                       slots, bounded ? kProbeLimitL1 : slots, flags, cursor + 3);
+    kern<<<blocks, kFastThreads4, smem>>>(key_col, static_cast<const VT*>(values), n, tab.as<FastSlot>(),
+                                          cnt.as<unsigned long long>(), slots - 1, slots,
+                                          bounded ? kProbeLimitL1 : slots, flags, cursor + 3);
   }
   B200_CHECK_LAST();
   if (bounded) {

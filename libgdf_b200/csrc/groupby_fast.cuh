@@ -1,42 +1,60 @@
-// Single-key group-by build kernel (v3).  Included by groupby.cu inside its anonymous namespace,
-// after FastSlot / fold() / hash_key() / smem_add64() are defined.
+// Single-key group-by build kernel (v4).  Included by groupby.cu inside its anonymous namespace,
+// after FastSlot / fold() / smem_add64() are defined.
 //
-// Changes against the first version, driven by profiles/r01_groupby_ncu.md:
-//   * work is handed out dynamically, 2048 rows per warp per grab (one global atomic per grab):
-//     with a static split 52 % of all warp samples sat at the final CTA barrier waiting for the
-//     slowest warps;
-//   * 2 CTAs x 768 threads per SM (48 warps) instead of 1 x 1024: the kernel is latency-bound
-//     (0.34 eligible warps per scheduler), so more resident warps hide more L2 latency; the per-CTA
-//     cache shrinks to 4096 slots (80 KB) to make room;
-//   * the first global-table slot of every row that missed the cache is loaded for all U rows of the
-//     step before any of them is resolved (U independent L2 requests in flight per thread).
+// History (profiles/r01a_ncu_full_summary.md): v3 ran C4 at 1.58 TB/s with the issue slots 70 % busy -
+// about 230 SASS instructions per row (MurmurHash3 per row, a 4-probe cache loop, a non-inlined
+// global fold, dynamically indexed register arrays that ptxas spilled to local memory).  The kernel was
+// instruction-bound, not memory-bound.  v4 is the same algorithm with the instruction count cut:
+//   * the table position comes from a 3-multiply mixer (the hash is internal: nothing observable
+//     depends on it, unlike gdf_hash / gdf_hash_partition which keep MurmurHash3);
+//   * the per-CTA cache is 2-way set associative and a set is ONE 128-bit shared-memory load;
+//   * rows are read with 128-bit loads (two 8-byte rows per load), four rows per lane per step,
+//     everything fully unrolled so that all per-row state stays in registers;
+//   * the op (sum / min / max), "count rows" and "keep a row count for AVG" are template parameters.
+// One CTA of 1024 threads per SM owns an 8192-slot cache (128 KB of shared memory); rows whose key is
+// not cached fold straight into the L2-resident global table with red.global.
 #pragma once
 
-constexpr int kFastThreads3 = 768;
-constexpr unsigned kCacheSlots3 = 4096;
-constexpr unsigned kCacheProbes3 = 4;
-constexpr int kFastU = 4;                                   // rows per thread per step
-constexpr unsigned kGrabRows = 32 * kFastU * 16;            // rows per warp per work grab
+constexpr int kFastThreads4 = 1024;
+constexpr unsigned kCacheSets4 = 4096;                 // x 2 ways
+constexpr unsigned kCacheSlots4 = 2 * kCacheSets4;
+constexpr unsigned kGrabRows4 = 32 * 4 * 32;           // rows per warp per work grab (4096)
 
-struct FastCache3 {
-  unsigned long long key[kCacheSlots3];
-  unsigned long long acc[kCacheSlots3];
-  unsigned cnt[kCacheSlots3];
+struct FastCache4 {
+  unsigned long long key[kCacheSlots4];   // way pairs are adjacent: one LDS.128 per set
+  unsigned long long acc[kCacheSlots4];
 };
 
-// Resolve one row against the global table, starting from an already loaded first slot key.
-static __device__ __noinline__ bool global_fold_from(FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt,
-                                                        unsigned mask, unsigned probe_limit, unsigned s,
-                                                        unsigned long long k0, unsigned long long key, int64_t v,
-                                                        unsigned long long c, int fold_op) {
+// Internal position hash.  h's top bits pick the cache set, its low bits the global slot.
+static __device__ __forceinline__ uint32_t mix_key(unsigned long long k) {
+  uint32_t x = (uint32_t)k * 0x9E3779B1u ^ (uint32_t)(k >> 32) * 0x85EBCA77u;
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  x ^= x >> 13;
+  return x;
+}
+
+template <int FOLD>
+static __device__ __forceinline__ void cache_fold(unsigned long long* acc, int64_t v) {
+  if (FOLD == OP_SUM) smem_add64(acc, v);
+  else if (FOLD == OP_MIN) atomicMin(reinterpret_cast<long long*>(acc), (long long)v);
+  else atomicMax(reinterpret_cast<long long*>(acc), (long long)v);
+}
+
+// Fold (v, c) for `key` into the global table starting at slot s whose key word `k0` is already loaded.
+template <int FOLD, bool WITH_CNT>
+static __device__ __forceinline__ bool global_fold4(FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt,
+                                                    unsigned mask, unsigned probe_limit, unsigned s,
+                                                    unsigned long long k0, unsigned long long key, int64_t v,
+                                                    unsigned long long c) {
   for (unsigned probe = 0; probe < probe_limit; ++probe) {
     if (k0 == kEmptyKey) {
       const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
       k0 = (prev == kEmptyKey) ? key : prev;
     }
     if (k0 == key) {
-      fold(&tab[s].acc, v, fold_op);
-      if (cnt) atomicAdd(&cnt[s], c);
+      fold(&tab[s].acc, v, FOLD);
+      if (WITH_CNT) atomicAdd(&cnt[s], c);
       return true;
     }
     s = (s + 1) & mask;
@@ -45,100 +63,121 @@ static __device__ __noinline__ bool global_fold_from(FastSlot* __restrict__ tab,
   return false;
 }
 
-template <typename KT, typename IT>
-__global__ void __launch_bounds__(kFastThreads3, 2)
-build_fast_kernel_v3(const KT* __restrict__ key_col, const IT* __restrict__ values, size_t n, int op,
+template <typename KT, typename IT, int FOLD, bool COUNT_ROWS, bool WITH_CNT>
+__global__ void __launch_bounds__(kFastThreads4, 1)
+build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ values, size_t n,
                      FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt, unsigned mask, unsigned slots,
                      unsigned probe_limit, int* __restrict__ flags /*[0]=side slot used, [1]=overflow*/,
                      unsigned long long* __restrict__ work_counter) {
   using UK = typename std::conditional<sizeof(KT) == 8, unsigned long long, unsigned>::type;
+  constexpr bool VEC = sizeof(KT) == 8 && sizeof(IT) == 8;  // two rows per 128-bit load
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FastCache3& cache = *reinterpret_cast<FastCache3*>(smem_raw);
-  const int fold_op = (op == OP_COUNT || op == OP_AVG) ? OP_SUM : op;
-  const bool additive = fold_op == OP_SUM;
-  const int64_t identity = op == OP_MIN ? (int64_t)std::numeric_limits<IT>::max()
-                                        : (op == OP_MAX ? (int64_t)std::numeric_limits<IT>::lowest() : 0);
-  for (unsigned i = threadIdx.x; i < kCacheSlots3; i += kFastThreads3) {
+  FastCache4& cache = *reinterpret_cast<FastCache4*>(smem_raw);
+  unsigned* ccnt = reinterpret_cast<unsigned*>(smem_raw + sizeof(FastCache4));  // only when WITH_CNT
+  const int64_t identity = FOLD == OP_MIN ? (int64_t)std::numeric_limits<IT>::max()
+                                          : (FOLD == OP_MAX ? (int64_t)std::numeric_limits<IT>::lowest() : 0);
+  for (unsigned i = threadIdx.x; i < kCacheSlots4; i += kFastThreads4) {
     cache.key[i] = kEmptyKey;
     cache.acc[i] = (unsigned long long)identity;
-    cache.cnt[i] = 0;
+    if (WITH_CNT) ccnt[i] = 0;
   }
   __syncthreads();
   const unsigned lane = lane_id();
+  const bool vec_ok = VEC && aligned16(key_col) && aligned16(values);
+
+  // one row: cache first, then the global table.  gk = key word of the row's first global slot,
+  // loaded by the caller for all rows of a step before any of them is resolved.
+  auto cache_try = [&](unsigned long long k, int64_t v, uint32_t h) -> bool {
+    const unsigned set = h >> 20;  // top 12 bits
+    const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(&cache.key[2 * set]);
+    int way = -1;
+    if (kk.x == k) way = 0;
+    else if (kk.y == k) way = 1;
+    else if (kk.x == kEmptyKey || kk.y == kEmptyKey) {  // cold start only: claim a free way
+      if (kk.x == kEmptyKey) {
+        const unsigned long long prev = atomicCAS(&cache.key[2 * set], kEmptyKey, k);
+        if (prev == kEmptyKey || prev == k) way = 0;
+      }
+      if (way < 0) {
+        const unsigned long long prev = atomicCAS(&cache.key[2 * set + 1], kEmptyKey, k);
+        if (prev == kEmptyKey || prev == k) way = 1;
+      }
+    }
+    if (way < 0) return false;
+    cache_fold<FOLD>(&cache.acc[2 * set + way], v);
+    if (WITH_CNT) atomicAdd(&ccnt[2 * set + way], 1u);
+    return true;
+  };
+
   while (true) {
     unsigned long long grab = 0;
     if (lane == 0) grab = atomicAdd(work_counter, 1ull);
     grab = __shfl_sync(0xffffffffu, grab, 0);
-    const size_t base = (size_t)grab * kGrabRows;
+    const size_t base = (size_t)grab * kGrabRows4;
     if (base >= n) break;
-    const size_t end = base + kGrabRows < n ? base + kGrabRows : n;
+    const size_t end = base + kGrabRows4 < n ? base + kGrabRows4 : n;
 #pragma unroll 1
-    for (size_t step = base; step < end; step += 32 * kFastU) {
-      unsigned long long k[kFastU];
-      int64_t v[kFastU];
-      uint32_t h[kFastU];
-      unsigned gs[kFastU];
-      unsigned long long gk[kFastU];
-      bool miss[kFastU];
+    for (size_t step = base; step < end; step += 128) {
+      unsigned long long k[4];
+      int64_t v[4];
+      bool live[4];
+      if (vec_ok && step + 128 <= end) {  // lane reads rows step + 2*lane (+1) and step + 64 + 2*lane (+1)
 #pragma unroll
-      for (int u = 0; u < kFastU; ++u) {
-        const size_t r = step + (size_t)u * 32 + lane;
-        const bool live = r < end;
-        k[u] = live ? (unsigned long long)(UK)key_col[r] : 0ull;
-        v[u] = (live && op != OP_COUNT) ? (int64_t)values[r] : 1;
-        miss[u] = live;
-        h[u] = 0;
-      }
-      // ---- phase 1: per-CTA shared-memory cache ----
-#pragma unroll
-      for (int u = 0; u < kFastU; ++u) {
-        if (!miss[u]) continue;
-        h[u] = hash_key<KT>(k[u]);
-        if (k[u] == kEmptyKey) continue;  // the EMPTY-pattern key is handled by the global side slot
-        unsigned s = (h[u] >> 7) & (kCacheSlots3 - 1);
-#pragma unroll
-        for (unsigned p = 0; p < kCacheProbes3; ++p, s = (s + 1) & (kCacheSlots3 - 1)) {
-          unsigned long long ck = cache.key[s];
-          if (ck == kEmptyKey) {
-            const unsigned long long prev = atomicCAS(&cache.key[s], kEmptyKey, k[u]);
-            ck = (prev == kEmptyKey) ? k[u] : prev;
+        for (int q = 0; q < 2; ++q) {
+          const size_t r = step + (size_t)q * 64 + 2 * lane;
+          const uint4 kr = ldg_stream(reinterpret_cast<const unsigned long long*>(key_col) + r);
+          k[2 * q] = ((unsigned long long)kr.y << 32) | kr.x;
+          k[2 * q + 1] = ((unsigned long long)kr.w << 32) | kr.z;
+          if (!COUNT_ROWS) {
+            const uint4 vr = ldg_stream(reinterpret_cast<const unsigned long long*>(values) + r);
+            v[2 * q] = (int64_t)(((unsigned long long)vr.y << 32) | vr.x);
+            v[2 * q + 1] = (int64_t)(((unsigned long long)vr.w << 32) | vr.z);
+          } else {
+            v[2 * q] = v[2 * q + 1] = 1;
           }
-          if (ck == k[u]) {
-            if (additive) smem_add64(&cache.acc[s], v[u]);
-            else if (fold_op == OP_MIN) atomicMin(reinterpret_cast<long long*>(&cache.acc[s]), (long long)v[u]);
-            else atomicMax(reinterpret_cast<long long*>(&cache.acc[s]), (long long)v[u]);
-            if (cnt) atomicAdd(&cache.cnt[s], 1u);
-            miss[u] = false;
-            break;
-          }
+          live[2 * q] = live[2 * q + 1] = true;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const size_t r = step + (size_t)u * 32 + lane;
+          live[u] = r < end;
+          k[u] = live[u] ? (unsigned long long)(UK)key_col[r] : 0ull;
+          v[u] = (live[u] && !COUNT_ROWS) ? (int64_t)values[r] : 1;
         }
       }
-      // ---- phase 2: rows that missed go to the L2-resident table; first slots fetched together ----
+      uint32_t h[4];
+      bool miss[4];
 #pragma unroll
-      for (int u = 0; u < kFastU; ++u) {
-        gs[u] = h[u] & mask;
-        gk[u] = (miss[u] && k[u] != kEmptyKey) ? tab[gs[u]].key : kEmptyKey;
+      for (int u = 0; u < 4; ++u) {
+        h[u] = mix_key(k[u]);
+        miss[u] = live[u];
+        if (live[u] && k[u] != kEmptyKey) miss[u] = !cache_try(k[u], v[u], h[u]);
       }
+      // rows that missed the cache: first global slots fetched together, then resolved
+      unsigned long long gk[4];
 #pragma unroll
-      for (int u = 0; u < kFastU; ++u) {
+      for (int u = 0; u < 4; ++u) gk[u] = (miss[u] && k[u] != kEmptyKey) ? tab[h[u] & mask].key : kEmptyKey;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
         if (!miss[u]) continue;
-        if (k[u] == kEmptyKey) {
-          fold(&tab[slots].acc, v[u], fold_op);
-          if (cnt) atomicAdd(&cnt[slots], 1ull);
+        if (k[u] == kEmptyKey) {  // a real key equal to the EMPTY pattern lives in the side slot
+          fold(&tab[slots].acc, v[u], FOLD);
+          if (WITH_CNT) atomicAdd(&cnt[slots], 1ull);
           flags[0] = 1;
-        } else if (!global_fold_from(tab, cnt, mask, probe_limit, gs[u], gk[u], k[u], v[u], 1ull, fold_op)) {
+        } else if (!global_fold4<FOLD, WITH_CNT>(tab, cnt, mask, probe_limit, h[u] & mask, gk[u], k[u], v[u], 1ull)) {
           flags[1] = 1;
         }
       }
     }
   }
   __syncthreads();
-  for (unsigned i = threadIdx.x; i < kCacheSlots3; i += kFastThreads3) {
+  for (unsigned i = threadIdx.x; i < kCacheSlots4; i += kFastThreads4) {
     const unsigned long long ck = cache.key[i];
     if (ck == kEmptyKey) continue;
-    const unsigned s = hash_key<KT>(ck) & mask;
-    if (!global_fold_from(tab, cnt, mask, probe_limit, s, tab[s].key, ck, (int64_t)cache.acc[i],
-                          (unsigned long long)cache.cnt[i], fold_op))
+    const unsigned s = mix_key(ck) & mask;
+    if (!global_fold4<FOLD, WITH_CNT>(tab, cnt, mask, probe_limit, s, tab[s].key, ck, (int64_t)cache.acc[i],
+                                      WITH_CNT ? (unsigned long long)ccnt[i] : 0ull))
       flags[1] = 1;
   }
 }

@@ -22,6 +22,7 @@
 //
 // Algorithmic bytes (C3): 8*(P+B) key bytes in, 8 bytes per output pair out.  Actual DRAM traffic of
 // this design: 2 reads of each key (histogram, scatter) + 12 B/row of pairs written and re-read.
+#include "stream.cuh"
 #include "table.cuh"
 
 namespace b200 {
@@ -45,17 +46,33 @@ struct alignas(16) Slot {
   int32_t pad;
 };
 
+// Internal position hash (partition id from its TOP bits, table slot from a re-mix).  Nothing
+// observable depends on it - gdf_hash / gdf_hash_partition keep MurmurHash3 - so it is a 3-multiply
+// mixer instead: MurmurHash3 cost ~25 of the ~35 instructions per row of the histogram pass, which made
+// that pass issue-bound at 4.2 TB/s (profiles/r01a_ncu_full_summary.md).
 template <typename KT> struct KeyBits;
 template <> struct KeyBits<uint64_t> {
-  static __device__ __forceinline__ uint32_t hash(uint64_t k) { return murmur3_32<8>(k); }
+  static __device__ __forceinline__ uint32_t hash(uint64_t k) {
+    uint32_t x = (uint32_t)k * 0x9E3779B1u ^ (uint32_t)(k >> 32) * 0x85EBCA77u;
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 13;
+    return x;
+  }
 };
 template <> struct KeyBits<uint32_t> {
-  static __device__ __forceinline__ uint32_t hash(uint32_t k) { return murmur3_32<4>(k); }
+  static __device__ __forceinline__ uint32_t hash(uint32_t k) {
+    uint32_t x = k * 0x9E3779B1u;
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 13;
+    return x;
+  }
 };
 
-// Slot index inside a partition's table: a re-mix of the row hash, so it is independent of the top bits
-// that chose the partition (all rows of one partition share those).
-static __device__ __forceinline__ uint32_t slot_hash(uint32_t h) { return fmix32(h + 0x9e3779b9u); }
+// Slot index inside a partition's table: all rows of one partition share the top bits of h, so the
+// slot comes from a multiplicative re-mix whose middle bits depend on every bit of h.
+static __device__ __forceinline__ uint32_t slot_hash(uint32_t h) { return (h * 0x9E3779B1u) >> 7; }
 
 struct PartGeom {
   unsigned nparts;  // power of two
@@ -217,28 +234,51 @@ part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[
   // One CTA = one contiguous tile of pairs, tiles dispatched in index order: the pairs are
   // partition-contiguous, so the CTAs in flight insert into one or two partitions' tables at a time
   // and those tables stay L2-resident (a grid-stride loop would touch every table at once).
+  // Each thread keeps kBuildU inserts in flight: the first CAS of every row is issued before any result
+  // is looked at (the v1 kernel did one dependent CAS round trip per row and sat at 12 % issue
+  // utilisation with 104 warps-per-issue stalled on the scoreboard).
+  constexpr int U = kBuildTile / kThreads;
   const size_t tile_lo = (size_t)blockIdx.x * kBuildTile;
-  const size_t tile_hi = tile_lo + kBuildTile < b.n ? tile_lo + kBuildTile : b.n;
-  for (size_t i = tile_lo + threadIdx.x; i < tile_hi; i += kThreads) {
-    int32_t row = b.rows ? b.rows[i] : (int32_t)i;
-    if (!b.rows && !bit_valid(b.valid, i)) continue;
-    const KT kraw = b.keys[i];
-    const unsigned long long key = (unsigned long long)kraw;
-    if (key == kEmptyKey) { flags[1] = 1; continue; }
-    const uint32_t h = KeyBits<KT>::hash(kraw);
-    const unsigned p = g.pid(h);
-    Slot* tab = t.slots + t.offset[p];
-    const unsigned mask = t.mask[p];
-    unsigned s = slot_hash(h) & mask;
-    while (true) {
-      const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
-      if (prev == kEmptyKey) {
-        tab[s].row = row;
-        break;
-      }
-      if (prev == key) flags[0] = 1;  // duplicate build key
-      s = (s + 1) & mask;
+  unsigned long long key[U], prev[U];
+  int32_t row[U];
+  Slot* tab[U];
+  unsigned s[U], mask[U];
+  bool live[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const size_t i = tile_lo + (size_t)u * kThreads + threadIdx.x;
+    live[u] = i < b.n;
+    key[u] = 0;
+    row[u] = 0;
+    if (live[u]) {
+      row[u] = b.rows ? b.rows[i] : (int32_t)i;
+      if (!b.rows && !bit_valid(b.valid, i)) live[u] = false;
+      key[u] = (unsigned long long)b.keys[i];
     }
+    if (live[u] && key[u] == kEmptyKey) {
+      flags[1] = 1;
+      live[u] = false;
+    }
+    const uint32_t h = KeyBits<KT>::hash((KT)key[u]);
+    const unsigned p = g.pid(h);
+    tab[u] = t.slots + t.offset[p];
+    mask[u] = t.mask[p];
+    s[u] = slot_hash(h) & mask[u];
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    prev[u] = live[u] ? atomicCAS(&tab[u][s[u]].key, kEmptyKey, key[u]) : kEmptyKey;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!live[u]) continue;
+    unsigned long long pv = prev[u];
+    unsigned at = s[u];
+    while (pv != kEmptyKey) {  // slot was taken: linear probing
+      if (pv == key[u]) flags[0] = 1;  // duplicate build key
+      at = (at + 1) & mask[u];
+      pv = atomicCAS(&tab[u][at].key, kEmptyKey, key[u]);
+    }
+    tab[u][at].row = row[u];
   }
 }
 
@@ -375,6 +415,230 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
   }
 }
 
+// ---- probe v2: persistent CTAs, TMA-staged pair tiles, two barriers per 2048-row tile ----
+//
+// profiles/r01a_ncu_full_summary.md, part_probe_kernel: 13.3 ms of the 25.2 ms C3 step, DRAM at 23 %,
+// issue slots 40 % busy (~195 instructions per row: MurmurHash3, four block-wide scans with two
+// barriers each per 1024-row tile), 14 warps-per-issue stalled on L2/DRAM latency with nothing
+// prefetched across tiles.  v2:
+//   * {key,tag} tiles arrive through a 3-stage cp.async.bulk ring (stream.cuh), L2 evict_first;
+//     table slots are read with an L2 evict_last hint so that streaming traffic does not push the
+//     hot partitions' tables out of L2;
+//   * a warp owns 256 consecutive rows of the tile, lane l handles rows i*32+l (i = 0..7): all eight
+//     slot lookups of a thread are issued before the first is consumed; ranks inside a warp come from
+//     ballots (0/1 matches) or a shuffle scan (duplicate build keys);
+//   * one cursor atomic and two barriers per tile; output stores of a warp step are consecutive ints.
+constexpr int kP2Threads = 256;
+constexpr int kP2Warps = kP2Threads / 32;
+constexpr int kP2Rows = 8;
+constexpr int kP2Tile = kP2Threads * kP2Rows;
+constexpr int kP2Stages = 3;
+
+template <typename KT>
+struct Probe2Geom {
+  static constexpr int kKeyBytes = kP2Tile * (int)sizeof(KT);
+  static constexpr int kTagBytes = kP2Tile * 4;
+  static constexpr int kStageBytes = kKeyBytes + kTagBytes;
+};
+struct Probe2Smem {
+  uint64_t bar[kP2Stages];
+  unsigned tile[kP2Stages];
+  unsigned warp_tot[2][kP2Warps];
+  unsigned long long tile_out[2];
+};
+template <typename KT>
+constexpr size_t probe2_smem_bytes() {
+  return (size_t)kP2Stages * Probe2Geom<KT>::kStageBytes + sizeof(Probe2Smem) + 128;
+}
+
+static __device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+static __device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+static __device__ __forceinline__ Slot ld_slot_hint(const Slot* p, uint64_t policy) {
+  uint4 raw;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+               : "l"(p), "l"(policy));
+  Slot s;
+  s.key = ((unsigned long long)raw.y << 32) | raw.x;
+  s.row = (int32_t)raw.z;
+  s.pad = 0;
+  return s;
+}
+static __device__ __forceinline__ void st_i32_hint(int32_t* p, int32_t v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
+}
+static __device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                      uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          tma::smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(tma::smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+template <typename KT, bool LEFT_LIKE, bool UNIQUE, bool WRITE>
+__global__ void __launch_bounds__(kP2Threads, 3)
+part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables t, int32_t* __restrict__ out_probe,
+                         int32_t* __restrict__ out_build, unsigned long long* __restrict__ cursor,
+                         unsigned* __restrict__ ticket) {
+  using G = Probe2Geom<KT>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  Probe2Smem& sm = *reinterpret_cast<Probe2Smem*>(ring + (size_t)kP2Stages * G::kStageBytes);
+  const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const size_t tiles = (pr.n + kP2Tile - 1) / kP2Tile;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_table = l2_policy_evict_last();
+
+  auto issue = [&](int s) {
+    const unsigned tl = atomicAdd(ticket, 1u);
+    sm.tile[s] = tl;
+    if ((size_t)tl < tiles && ((size_t)tl + 1) * kP2Tile <= pr.n) {
+      unsigned char* dst = ring + (size_t)s * G::kStageBytes;
+      tma::mbar_expect_tx(&sm.bar[s], G::kStageBytes);
+      bulk_load_hint(dst, pr.keys + (size_t)tl * kP2Tile, G::kKeyBytes, &sm.bar[s], pol_stream);
+      bulk_load_hint(dst + G::kKeyBytes, pr.rows + (size_t)tl * kP2Tile, G::kTagBytes, &sm.bar[s], pol_stream);
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kP2Stages; ++s) tma::mbar_init(&sm.bar[s], 1);
+    tma::fence_barrier_init();
+#pragma unroll
+    for (int s = 0; s < kP2Stages; ++s) issue(s);
+  }
+  __syncthreads();
+
+  for (unsigned iter = 0;; ++iter) {
+    const int s = (int)(iter % kP2Stages);
+    const unsigned tl = sm.tile[s];
+    if ((size_t)tl >= tiles) break;
+    const size_t tile_row0 = (size_t)tl * kP2Tile;
+    const bool full = tile_row0 + kP2Tile <= pr.n;
+    unsigned long long key[kP2Rows];
+    int32_t prow[kP2Rows], first[kP2Rows];
+    unsigned cnt[kP2Rows], where[kP2Rows];  // where = partition id << 24 | first slot (slots <= 2^24 per table)
+    bool lookup[kP2Rows];
+    if (full) tma::mbar_wait(&sm.bar[s], (iter / kP2Stages) & 1u);
+    const KT* skeys = reinterpret_cast<const KT*>(ring + (size_t)s * G::kStageBytes);
+    const int32_t* stags = reinterpret_cast<const int32_t*>(ring + (size_t)s * G::kStageBytes + G::kKeyBytes);
+#pragma unroll
+    for (int i = 0; i < kP2Rows; ++i) {
+      const unsigned local = warp * (32 * kP2Rows) + i * 32 + lane;
+      const size_t j = tile_row0 + local;
+      bool have = full || j < pr.n;
+      KT kraw = 0;
+      int32_t tag = 0;
+      if (full) {
+        kraw = skeys[local];
+        tag = stags[local];
+      } else if (have) {
+        kraw = pr.keys[j];
+        tag = pr.rows[j];
+      }
+      key[i] = (unsigned long long)kraw;
+      const bool ok = have && tag >= 0;  // negative tag = NULL-key row kept for LEFT/FULL
+      prow[i] = tag >= 0 ? tag : ~tag;
+      first[i] = -1;
+      cnt[i] = (LEFT_LIKE && have) ? 1u : 0u;
+      lookup[i] = ok && key[i] != kEmptyKey;
+      const uint32_t h = KeyBits<KT>::hash(kraw);
+      const unsigned p = g.pid(h);
+      where[i] = (p << 24) | (slot_hash(h) & t.mask[p]);
+    }
+    Slot s0[kP2Rows];
+#pragma unroll
+    for (int i = 0; i < kP2Rows; ++i)
+      if (lookup[i]) s0[i] = ld_slot_hint(t.slots + t.offset[where[i] >> 24] + (where[i] & 0xffffffu), pol_table);
+#pragma unroll
+    for (int i = 0; i < kP2Rows; ++i) {
+      if (!lookup[i]) continue;
+      unsigned c = 0;
+      Slot cur = s0[i];
+      if (cur.key == key[i] && UNIQUE) {  // common case: first slot, no chain
+        first[i] = cur.row;
+        cnt[i] = 1;
+        continue;
+      }
+      const Slot* tb = t.slots + t.offset[where[i] >> 24];
+      const unsigned m = t.mask[where[i] >> 24];
+      unsigned at = where[i] & 0xffffffu;
+      while (cur.key != kEmptyKey) {
+        if (cur.key == key[i]) {
+          if (c == 0) first[i] = cur.row;
+          ++c;
+          if (UNIQUE) break;
+        }
+        at = (at + 1) & m;
+        cur = ld_slot_hint(tb + at, pol_table);
+      }
+      if (c) cnt[i] = c;
+    }
+    // ranks: step-major inside the warp, then warps, then the tile's reservation
+    unsigned rank[kP2Rows], warp_total = 0;
+#pragma unroll
+    for (int i = 0; i < kP2Rows; ++i) {
+      if (UNIQUE) {  // counts are 0/1
+        const unsigned b = __ballot_sync(0xffffffffu, cnt[i] != 0);
+        rank[i] = warp_total + __popc(b & lanemask_lt());
+        warp_total += __popc(b);
+      } else {
+        unsigned inc = cnt[i];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= (unsigned)d) inc += o;
+        }
+        rank[i] = warp_total + inc - cnt[i];
+        warp_total += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    const unsigned buf = iter & 1u;
+    if (lane == 0) sm.warp_tot[buf][warp] = warp_total;
+    __syncthreads();  // stage s is consumed; warp totals visible
+    if (tid == 32) issue(s);
+    if (tid == 0) {
+      unsigned tot = 0;
+#pragma unroll
+      for (int w = 0; w < kP2Warps; ++w) tot += sm.warp_tot[buf][w];
+      sm.tile_out[buf] = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
+    }
+    if (!WRITE) continue;  // count-only pass: the cursor is the result (tile_out is double-buffered)
+    __syncthreads();
+    size_t pos0 = (size_t)sm.tile_out[buf];
+    for (unsigned w = 0; w < warp; ++w) pos0 += sm.warp_tot[buf][w];
+#pragma unroll
+    for (int i = 0; i < kP2Rows; ++i) {
+      size_t pos = pos0 + rank[i];
+      if (cnt[i] == 1) {
+        st_i32_hint(out_probe + pos, prow[i], pol_stream);
+        st_i32_hint(out_build + pos, first[i], pol_stream);
+      } else if (cnt[i] > 1) {
+        const Slot* tb = t.slots + t.offset[where[i] >> 24];
+        const unsigned m = t.mask[where[i] >> 24];
+        unsigned at = where[i] & 0xffffffu;
+        Slot cur = ld_slot_hint(tb + at, pol_table);
+        while (cur.key != kEmptyKey) {
+          if (cur.key == key[i]) {
+            out_probe[pos] = prow[i];
+            out_build[pos] = cur.row;
+            ++pos;
+          }
+          at = (at + 1) & m;
+          cur = ld_slot_hint(tb + at, pol_table);
+        }
+      }
+    }
+  }
+}
+
 __global__ void mark_rows_kernel(const int32_t* __restrict__ idx, size_t n, unsigned char* __restrict__ marks,
                                  size_t limit) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -464,12 +728,35 @@ gdf_error read_u64(const unsigned long long* d, unsigned long long* h) {
   return GDF_SUCCESS;
 }
 
+template <typename KT, bool LEFT_LIKE, bool UNIQUE, bool WRITE>
+gdf_error launch_probe_stream(const Pairs<KT>& pr, PartGeom g, const Tables& t, int32_t* op, int32_t* ob,
+                              unsigned long long* cursor, unsigned* ticket) {
+  auto kern = part_probe_stream_kernel<KT, LEFT_LIKE, UNIQUE, WRITE>;
+  const int smem = (int)probe2_smem_bytes<KT>();
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), 0));
+  const size_t tiles = (pr.n + kP2Tile - 1) / kP2Tile;
+  const size_t resident = (size_t)sm_count() * (sizeof(KT) == 8 ? 3 : 4);
+  const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
+  kern<<<blocks, kP2Threads, smem>>>(pr, g, t, op, ob, cursor, ticket);
+  B200_CHECK_LAST();
+  return GDF_SUCCESS;
+}
+
 template <typename KT, bool LEFT_LIKE>
 gdf_error launch_probe(bool unique, bool write, const Pairs<KT>& pr, PartGeom g, const Tables& t, int32_t* op,
-                       int32_t* ob, unsigned long long* cursor) {
-  const unsigned tiles = (unsigned)((pr.n + kProbeTile - 1) / kProbeTile);
-  if (tiles == 0) return GDF_SUCCESS;
+                       int32_t* ob, unsigned long long* cursor, unsigned* ticket, bool stream_ok) {
+  if (pr.n == 0) return GDF_SUCCESS;
   B200_TIMED(write ? "join_part_probe" : "join_part_count");
+  if (pr.rows != nullptr && stream_ok) {  // partitioned {key,tag} pairs: streaming kernel
+    if (unique) {
+      if (write) return launch_probe_stream<KT, LEFT_LIKE, true, true>(pr, g, t, op, ob, cursor, ticket);
+      return launch_probe_stream<KT, LEFT_LIKE, true, false>(pr, g, t, op, ob, cursor, ticket);
+    }
+    if (write) return launch_probe_stream<KT, LEFT_LIKE, false, true>(pr, g, t, op, ob, cursor, ticket);
+    return launch_probe_stream<KT, LEFT_LIKE, false, false>(pr, g, t, op, ob, cursor, ticket);
+  }
+  const unsigned tiles = (unsigned)((pr.n + kProbeTile - 1) / kProbeTile);
   if (unique) {
     if (write) part_probe_kernel<KT, LEFT_LIKE, true, true><<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
     else part_probe_kernel<KT, LEFT_LIKE, true, false><<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
@@ -501,13 +788,14 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
     g.shift = 32 - lg;
   }
   Scratch small;  // totals[np] | cursors[np] | toffset[np] | tmask[np] | cursor | flags
-  const size_t small_bytes = g.nparts * (3 * sizeof(unsigned long long) + sizeof(unsigned)) + 64;
+  const size_t small_bytes = g.nparts * (3 * sizeof(unsigned long long) + sizeof(unsigned)) + 64;  // 64 = cursor|flags|ticket|pad
   B200_CUDA_TRY(small.alloc(small_bytes));
   unsigned long long* d_totals = small.as<unsigned long long>();
   unsigned long long* d_cursors = d_totals + g.nparts;
   unsigned long long* d_toffset = d_cursors + g.nparts;
   unsigned long long* d_cursor = d_toffset + g.nparts;
   int* d_flags = reinterpret_cast<int*>(d_cursor + 1);
+  unsigned* d_ticket = reinterpret_cast<unsigned*>(d_cursor + 3);
   unsigned* d_tmask = reinterpret_cast<unsigned*>(d_cursor + 4);
   B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 4 * sizeof(unsigned long long), 0));
 
@@ -531,8 +819,10 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   // one table per partition, sized from the actual counts (load factor <= 0.5)
   unsigned long long h_toffset[kMaxParts], total_slots = 0;
   unsigned h_tmask[kMaxParts];
+  bool stream_ok = true;  // the streaming probe packs {partition, slot} into 8 + 24 bits
   for (unsigned p = 0; p < g.nparts; ++p) {
     const unsigned slots = pow2_at_least(h_btot[p] ? 2 * h_btot[p] : 2);
+    if (slots > (1u << 24)) stream_ok = false;
     h_toffset[p] = total_slots;
     h_tmask[p] = slots - 1;
     total_slots += slots;
@@ -563,8 +853,8 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   size_t bound = pp.n;
   gdf_error e = GDF_SUCCESS;
   if (!unique) {
-    e = left_like ? launch_probe<KT, true>(false, false, pp, g, t, nullptr, nullptr, d_cursor)
-                  : launch_probe<KT, false>(false, false, pp, g, t, nullptr, nullptr, d_cursor);
+    e = left_like ? launch_probe<KT, true>(false, false, pp, g, t, nullptr, nullptr, d_cursor, d_ticket, stream_ok)
+                  : launch_probe<KT, false>(false, false, pp, g, t, nullptr, nullptr, d_cursor, d_ticket, stream_ok);
     if (e != GDF_SUCCESS) return e;
     unsigned long long exact = 0;
     if ((e = read_u64(d_cursor, &exact)) != GDF_SUCCESS) return e;
@@ -584,8 +874,8 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
     rmmFree(op, 0);
     return GDF_MEMORYMANAGER_ERROR;
   }
-  e = left_like ? launch_probe<KT, true>(unique, true, pp, g, t, op, ob, d_cursor)
-                : launch_probe<KT, false>(unique, true, pp, g, t, op, ob, d_cursor);
+  e = left_like ? launch_probe<KT, true>(unique, true, pp, g, t, op, ob, d_cursor, d_ticket, stream_ok)
+                : launch_probe<KT, false>(unique, true, pp, g, t, op, ob, d_cursor, d_ticket, stream_ok);
   unsigned long long found = 0;
   if (e == GDF_SUCCESS) e = read_u64(d_cursor, &found);
   if (e == GDF_SUCCESS && kind == JOIN_FULL) {

@@ -1,0 +1,98 @@
+"""-m gpu: the per-shard operators of the multi-GPU layer (libgdf_b200.dist.GdfOps: gdf_hash_partition,
+gdf_inner_join / gdf_left_join + gdfx_remap_indices, gdf_group_by_sum) on ONE GPU, with the all-to-all
+emulated in-process: R virtual ranks partition their shards, the partitions are regrouped by
+destination exactly as dist.exchange would deliver them, and every virtual rank runs its local operator.
+The union must equal the single-table oracle result.  (The real exchange is covered by
+tests/test_dist_cpu.py under gloo, and by bench.py --gpus N under NCCL.)"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from libgdf_b200 import dist as D
+
+pytestmark = pytest.mark.gpu
+
+
+def _emulated_exchange(per_rank_cols, per_rank_offsets, world):
+    """per_rank_cols[r] = partition-contiguous columns of rank r -> received columns per destination."""
+    recv = []
+    for dst in range(world):
+        cols = []
+        for c in range(len(per_rank_cols[0])):
+            parts = []
+            for src in range(world):
+                n = per_rank_cols[src][c].numel()
+                b = list(per_rank_offsets[src]) + [n]
+                parts.append(per_rank_cols[src][c][b[dst]:b[dst + 1]])
+            cols.append(torch.cat(parts))
+        recv.append(cols)
+    return recv
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("kind", ["inner", "left"])
+def test_sharded_join_matches_oracle(world, kind):
+    ops = D.GdfOps()
+    P, B = 400_000, 50_000
+    probe = np.random.randint(0, 2 * B, P).astype(np.int64)
+    build = np.random.permutation(B).astype(np.int64)
+    if kind == "left":
+        build = np.concatenate([build, build[:500]])
+    shards_l, shards_r, offs_l, offs_r = [], [], [], []
+    for r in range(world):
+        plo, phi = D.shard_bounds(len(probe), world, r)
+        blo, bhi = D.shard_bounds(len(build), world, r)
+        lk = torch.from_numpy(probe[plo:phi]).cuda()
+        rk = torch.from_numpy(build[blo:bhi]).cuda()
+        lid = torch.arange(plo, phi, dtype=torch.int32, device="cuda")
+        rid = torch.arange(blo, bhi, dtype=torch.int32, device="cuda")
+        cl, ol = ops.hash_partition([lk, lid], world)
+        cr, orr = ops.hash_partition([rk, rid], world)
+        shards_l.append(cl), offs_l.append(ol), shards_r.append(cr), offs_r.append(orr)
+    recv_l = _emulated_exchange(shards_l, offs_l, world)
+    recv_r = _emulated_exchange(shards_r, offs_r, world)
+    got_l, got_r = [], []
+    for r in range(world):
+        fn = ops.inner_join if kind == "inner" else ops.left_join
+        gl, gr = fn(recv_l[r][0], recv_r[r][0], recv_l[r][1], recv_r[r][1])
+        got_l.append(gl.cpu().numpy()), got_r.append(gr.cpu().numpy())
+    gl, gr = np.concatenate(got_l), np.concatenate(got_r)
+    ol, orr = oracle.join(oracle.JOIN_INNER if kind == "inner" else oracle.JOIN_LEFT, [probe], [build])
+    got = np.stack([gl, gr], 1)
+    want = np.stack([ol, orr], 1)
+    np.testing.assert_array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_groupby_matches_oracle(world):
+    ops = D.GdfOps()
+    N, G = 600_000, 3000
+    keys = (np.random.zipf(1.2, N) % G).astype(np.int64) * 7919 + 13
+    vals = np.random.randint(0, 1000, N).astype(np.int64)
+    partial_cols, partial_offs = [], []
+    for r in range(world):
+        lo, hi = D.shard_bounds(N, world, r)
+        pk, pv = ops.group_by_sum(torch.from_numpy(keys[lo:hi]).cuda(), torch.from_numpy(vals[lo:hi]).cuda())
+        cols, off = ops.hash_partition([pk.contiguous(), pv.contiguous()], world)
+        partial_cols.append(cols), partial_offs.append(off)
+    recv = _emulated_exchange(partial_cols, partial_offs, world)
+    gk, gv = [], []
+    for r in range(world):
+        k, v = ops.group_by_sum(recv[r][0], recv[r][1])
+        gk.append(k.cpu().numpy()), gv.append(v.cpu().numpy())
+    gk, gv = np.concatenate(gk), np.concatenate(gv)
+    ok, oa = oracle.groupby(oracle.OP_SUM, [keys], vals)
+    assert len(np.unique(gk)) == len(gk), "a key landed on two ranks"
+    assert sorted(zip(gk.tolist(), gv.tolist())) == sorted(zip(ok[0].tolist(), oa.tolist()))
+
+
+def test_remap_indices_keeps_minus_one():
+    from libgdf_b200 import columns as C
+    from libgdf_b200.libgdf_cffi import ffi, libgdf
+    idx = torch.tensor([0, -1, 3, 2, -1, 1], dtype=torch.int32, device="cuda")
+    payload = torch.tensor([100, 101, 102, 103], dtype=torch.int32, device="cuda")
+    col = C.Column(idx)
+    libgdf.gdfx_remap_indices(col.cdata, ffi.cast("int32_t*", payload.data_ptr()), payload.numel())
+    torch.cuda.synchronize()
+    assert idx.cpu().tolist() == [100, -1, 103, 102, -1, 101]
