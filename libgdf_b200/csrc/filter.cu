@@ -176,24 +176,26 @@ gdf_error read_count(const unsigned long long* d_count, size_t* h_count) {
 template <typename T>
 gdf_error run_filter_stream(const T* data, size_t n, const void* const* d_vals, size_t* out, size_t* h_count) {
   using G = select_stream::Geom<T>;
-  const size_t tiles = (n + G::kTileRows - 1) / G::kTileRows;
-  B200_REQUIRE(tiles < (1ull << 31), GDF_COLUMN_SIZE_TOO_BIG);
-  Scratch desc;  // [tiles] look-back descriptors | selected count | ticket counter
-  const size_t bytes = tiles * sizeof(uint64_t) + 2 * sizeof(unsigned long long);
+  const size_t chunks = (n + G::kChunkRows - 1) / G::kChunkRows;
+  B200_REQUIRE(chunks < (1ull << 31), GDF_COLUMN_SIZE_TOO_BIG);
+  Scratch desc;  // [chunks] look-back descriptors | selected count
+  const size_t bytes = chunks * sizeof(uint64_t) + sizeof(unsigned long long);
   B200_CUDA_TRY(desc.alloc(bytes));
   B200_CUDA_TRY(cudaMemsetAsync(desc.ptr, 0, bytes, 0));
   uint64_t* d = desc.as<uint64_t>();
-  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + tiles);
-  unsigned* ticket = reinterpret_cast<unsigned*>(d_count + 1);
+  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + chunks);
   auto kern = select_stream::select_stream_kernel<T, EqualsDeviceScalar<T>, EmitRowIndex>;
   const int smem = (int)select_stream::smem_bytes<T>();
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const size_t resident = (size_t)sm_count() * 2;  // 2 CTAs x ~97 KB of shared memory per SM
-  const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
+  int per_sm = 0;  // the look-back needs every CTA of the grid to be co-resident
+  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, select_stream::kThreads, smem));
+  B200_REQUIRE(per_sm >= 1, GDF_CUDA_ERROR);
+  const size_t resident = (size_t)sm_count() * (size_t)per_sm;
+  const unsigned blocks = (unsigned)(chunks < resident ? chunks : resident);
   {
     B200_TIMED("select");
     kern<<<blocks, select_stream::kThreads, smem>>>(data, n, EqualsDeviceScalar<T>{d_vals, T()}, EmitRowIndex{out}, d,
-                                                    ticket, d_count);
+                                                    d_count);
   }
   B200_CHECK_LAST();
   return read_count(d_count, h_count);

@@ -22,6 +22,8 @@
 //
 // Algorithmic bytes (C3): 8*(P+B) key bytes in, 8 bytes per output pair out.  Actual DRAM traffic of
 // this design: 2 reads of each key (histogram, scatter) + 12 B/row of pairs written and re-read.
+#include <cstdlib>
+
 #include "stream.cuh"
 #include "table.cuh"
 
@@ -72,7 +74,8 @@ template <> struct KeyBits<uint32_t> {
 
 // Slot index inside a partition's table: all rows of one partition share the top bits of h, so the
 // slot comes from a multiplicative re-mix whose middle bits depend on every bit of h.
-static __device__ __forceinline__ uint32_t slot_hash(uint32_t h) { return (h * 0x9E3779B1u) >> 7; }
+// Home slots are EVEN: a probe reads the aligned 32-byte pair {home, home+1} in one sector.
+static __device__ __forceinline__ uint32_t slot_hash(uint32_t h) { return ((h * 0x9E3779B1u) >> 7) & ~1u; }
 
 struct PartGeom {
   unsigned nparts;  // power of two
@@ -90,21 +93,46 @@ part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__
   __shared__ unsigned hist[kMaxParts];
   for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) hist[p] = 0;
   __syncthreads();
-  constexpr int U = 8;
   const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t r0 = (size_t)blockIdx.x * kThreads + threadIdx.x; r0 < n; r0 += stride * U) {
-    KT k[U];
+  if (valid == nullptr && aligned16(keys)) {  // no mask: 128-bit loads, 4 in flight per thread
+    constexpr int VEC = 16 / (int)sizeof(KT), U = 4;
+    const size_t nvec = n / VEC;
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    for (size_t v0 = (size_t)blockIdx.x * kThreads + threadIdx.x; v0 < nvec; v0 += stride * U) {
+      uint4 raw[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t r = r0 + (size_t)u * stride;
-      k[u] = r < n ? keys[r] : (KT)0;
+      for (int u = 0; u < U; ++u) {
+        const size_t v = v0 + (size_t)u * stride;
+        raw[u] = v < nvec ? ldg_stream(k4 + v) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (v0 + (size_t)u * stride >= nvec) continue;
+        const KT* e = reinterpret_cast<const KT*>(&raw[u]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(e[j]))], 1u);
+      }
     }
+    if (blockIdx.x == 0 && threadIdx.x < VEC) {  // ragged tail
+      const size_t r = nvec * VEC + threadIdx.x;
+      if (r < n) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(keys[r]))], 1u);
+    }
+  } else {
+    constexpr int U = 8;
+    for (size_t r0 = (size_t)blockIdx.x * kThreads + threadIdx.x; r0 < n; r0 += stride * U) {
+      KT k[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t r = r0 + (size_t)u * stride;
-      if (r >= n) continue;
-      if (bit_valid(valid, r)) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(k[u]))], 1u);
-      else if (KEEP_NULLS) atomicAdd(&hist[(unsigned)r & (g.nparts - 1)], 1u);
+      for (int u = 0; u < U; ++u) {
+        const size_t r = r0 + (size_t)u * stride;
+        k[u] = r < n ? keys[r] : (KT)0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t r = r0 + (size_t)u * stride;
+        if (r >= n) continue;
+        if (bit_valid(valid, r)) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(k[u]))], 1u);
+        else if (KEEP_NULLS) atomicAdd(&hist[(unsigned)r & (g.nparts - 1)], 1u);
+      }
     }
   }
   __syncthreads();
@@ -113,19 +141,28 @@ part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__
 }
 
 // ---- pass 2: write-combining scatter of {key,row} pairs ----
+// v2 (profiles/r01a: v1 reached 3.8 TB/s of DRAM traffic with six barriers per 4096-row tile, 24 warps
+// per SM and the tile's loads issued only after the previous tile had been written):
+//   * the NEXT tile's keys are loaded into registers before the current tile is ranked, so DRAM
+//     latency overlaps the shared-memory phases;
+//   * three barriers per tile: rank (shared-memory atomics) | reserve runs (one global atomic per
+//     non-empty partition, issued early and only consumed after the staging phase) + scan | stage |
+//     copy-out;
+//   * copy-out is warp-per-partition: a warp copies one partition's run of the staged tile to its
+//     reserved global range with consecutive lanes on consecutive elements - no per-element
+//     partition lookup, coalesced stores.
 template <typename KT>
 struct ScatterSmem {
   KT keys[kScatterTile];
   int32_t rows[kScatterTile];
-  unsigned short pid[kScatterTile];
-  unsigned hist[kMaxParts];                  // rows of this tile per partition
+  unsigned short pid[kScatterTile];          // partition of every staged element (element-parallel copy-out)
+  unsigned hist[2][kMaxParts];               // rows of this tile per partition (double-buffered)
   unsigned lstart[kMaxParts];                // start of partition p inside the staged tile
   unsigned long long gbase[kMaxParts];       // reserved global start of this tile's run
-  unsigned kept;
 };
 
-template <typename KT, bool KEEP_NULLS>
-__global__ void __launch_bounds__(kThreads)
+template <typename KT, bool KEEP_NULLS, bool PREFETCH>
+__global__ void __launch_bounds__(kThreads, PREFETCH ? 2 : 3)
 part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
                     unsigned long long* __restrict__ cursors, KT* __restrict__ out_keys,
                     int32_t* __restrict__ out_rows) {
@@ -133,19 +170,28 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
   ScatterSmem<KT>& sm = *reinterpret_cast<ScatterSmem<KT>*>(smem_raw);
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   const size_t tiles = (n + kScatterTile - 1) / kScatterTile;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const size_t base = tile * kScatterTile;
-    for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) sm.hist[p] = 0;
-    __syncthreads();
-    KT k[kScatterRows];
-    unsigned rp[kScatterRows];  // rank << 16 | pid, pid 0xffff = dropped, bit 15 = NULL-key row
-    // a warp owns 32*kScatterRows consecutive rows; step i covers 32 consecutive rows (coalesced)
-    const size_t wbase = base + (size_t)warp * (32 * kScatterRows);
+  for (unsigned p = threadIdx.x; p < 2 * kMaxParts; p += kThreads) (&sm.hist[0][0])[p] = 0;
+  __syncthreads();
+  KT knext[kScatterRows];
+  // a warp owns 32*kScatterRows consecutive rows; step i covers 32 consecutive rows (coalesced)
+  auto load_tile = [&](size_t tile) {
+    const size_t wbase = tile * kScatterTile + (size_t)warp * (32 * kScatterRows);
 #pragma unroll
     for (int i = 0; i < kScatterRows; ++i) {
       const size_t r = wbase + (size_t)i * 32 + lane;
-      k[i] = r < n ? keys[r] : (KT)0;
+      knext[i] = (tile < tiles && r < n) ? keys[r] : (KT)0;
     }
+  };
+  if (PREFETCH) load_tile(blockIdx.x);
+  unsigned buf = 0;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1u) {
+    const size_t wbase = tile * kScatterTile + (size_t)warp * (32 * kScatterRows);
+    KT k[kScatterRows];
+    if (!PREFETCH) load_tile(tile);
+#pragma unroll
+    for (int i = 0; i < kScatterRows; ++i) k[i] = knext[i];
+    if (PREFETCH) load_tile(tile + gridDim.x);  // in flight during all the shared-memory phases below
+    unsigned rp[kScatterRows];    // rank << 16 | pid, 0xffff = dropped, bit 15 = NULL-key row
 #pragma unroll
     for (int i = 0; i < kScatterRows; ++i) {
       const size_t r = wbase + (size_t)i * 32 + lane;
@@ -156,40 +202,40 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
         else if (KEEP_NULLS) { p = (unsigned)r & (g.nparts - 1); nullbit = 0x8000u; }
         else keep = false;
       }
-      rp[i] = keep ? ((atomicAdd(&sm.hist[p], 1u) << 16) | p | nullbit) : 0xffffu;
+      rp[i] = keep ? ((atomicAdd(&sm.hist[buf][p], 1u) << 16) | p | nullbit) : 0xffffu;
     }
-    __syncthreads();
-    // per partition: reserve this tile's run in the global output with one atomic
-    for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) {
-      const unsigned run = sm.hist[p];
-      sm.lstart[p] = run;  // count for now, scanned below
-      sm.gbase[p] = run ? atomicAdd(&cursors[p], (unsigned long long)run) : 0ull;
+    __syncthreads();  // (1) tile histogram complete
+    {                 // reserve this tile's runs: result lands in gbase[] before barrier (3)
+      const unsigned p = threadIdx.x;
+      if (p < g.nparts) {
+        const unsigned run = sm.hist[buf][p];
+        sm.gbase[p] = run ? atomicAdd(&cursors[p], (unsigned long long)run) : 0ull;
+      }
+      sm.hist[buf ^ 1u][threadIdx.x] = 0;  // kThreads == kMaxParts: clear the other buffer for the next tile
     }
-    __syncthreads();
-    if (warp == 0) {  // exclusive scan of the <= 256 partition counts (8 per lane)
-      unsigned c[kMaxParts / 32], s = 0;
+    if (warp == kThreads / 32 - 1) {  // exclusive scan of the <= 256 partition counts (8 per lane)
+      unsigned c[kMaxParts / 32], tot = 0;
 #pragma unroll
       for (int j = 0; j < (int)(kMaxParts / 32); ++j) {
         const unsigned p = lane * (kMaxParts / 32) + j;
-        c[j] = p < g.nparts ? sm.lstart[p] : 0;
-        s += c[j];
+        c[j] = p < g.nparts ? sm.hist[buf][p] : 0;
+        tot += c[j];
       }
-      unsigned inc = s;
+      unsigned inc = tot;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= (unsigned)d) inc += o;
       }
-      unsigned run = inc - s;
+      unsigned run = inc - tot;
 #pragma unroll
       for (int j = 0; j < (int)(kMaxParts / 32); ++j) {
         const unsigned p = lane * (kMaxParts / 32) + j;
         if (p < g.nparts) sm.lstart[p] = run;
         run += c[j];
       }
-      if (lane == 31) sm.kept = inc;
     }
-    __syncthreads();
+    __syncthreads();  // (2) lstart visible (previous tile's copy-out finished before barrier (1))
 #pragma unroll
     for (int i = 0; i < kScatterRows; ++i) {
       if ((rp[i] & 0xffffu) == 0xffffu) continue;
@@ -200,15 +246,19 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
       sm.rows[at] = (rp[i] & 0x8000u) ? ~r : r;
       sm.pid[at] = (unsigned short)p;
     }
-    __syncthreads();
-    const unsigned kept = sm.kept;
-    for (unsigned j = threadIdx.x; j < kept; j += kThreads) {
-      const unsigned p = sm.pid[j];
-      const unsigned long long gidx = sm.gbase[p] + (j - sm.lstart[p]);
-      out_keys[gidx] = sm.keys[j];
-      out_rows[gidx] = sm.rows[j];
+    __syncthreads();  // (3) staged tile + gbase complete
+    {  // element-parallel copy-out: consecutive threads take consecutive staged elements, which are
+       // consecutive in the output wherever they belong to the same partition
+      const unsigned kept = sm.lstart[g.nparts - 1] + sm.hist[buf][g.nparts - 1];
+      for (unsigned j = threadIdx.x; j < kept; j += kThreads) {
+        const unsigned p = sm.pid[j];
+        const unsigned long long gidx = sm.gbase[p] + (j - sm.lstart[p]);
+        out_keys[gidx] = sm.keys[j];
+        out_rows[gidx] = sm.rows[j];
+      }
     }
-    __syncthreads();
+    // the next iteration's barrier (1) separates this copy-out from the next staging phase; the
+    // histogram of this tile (hist[buf]) is cleared during the NEXT tile's phase (2)
   }
 }
 
@@ -265,20 +315,28 @@ part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[
     mask[u] = t.mask[p];
     s[u] = slot_hash(h) & mask[u];
   }
+  // Rounds: every still-pending insert of the thread issues its CAS, then all results are examined.
+  // (Resolving row after row makes a warp pay max-over-32-lanes of the probe length once PER ROW: the
+  // first version of this loop spent 34 warps-per-issue on the scoreboard.)
+  unsigned pend = 0;
 #pragma unroll
   for (int u = 0; u < U; ++u)
-    prev[u] = live[u] ? atomicCAS(&tab[u][s[u]].key, kEmptyKey, key[u]) : kEmptyKey;
+    if (live[u]) pend |= 1u << u;
+  while (pend) {
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    if (!live[u]) continue;
-    unsigned long long pv = prev[u];
-    unsigned at = s[u];
-    while (pv != kEmptyKey) {  // slot was taken: linear probing
-      if (pv == key[u]) flags[0] = 1;  // duplicate build key
-      at = (at + 1) & mask[u];
-      pv = atomicCAS(&tab[u][at].key, kEmptyKey, key[u]);
+    for (int u = 0; u < U; ++u)
+      if ((pend >> u) & 1u) prev[u] = atomicCAS(&tab[u][s[u]].key, kEmptyKey, key[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!((pend >> u) & 1u)) continue;
+      if (prev[u] == kEmptyKey) {  // claimed
+        tab[u][s[u]].row = row[u];
+        pend &= ~(1u << u);
+      } else {
+        if (prev[u] == key[u]) flags[0] = 1;  // duplicate build key
+        s[u] = (s[u] + 1) & mask[u];         // linear probing
+      }
     }
-    tab[u][at].row = row[u];
   }
 }
 
@@ -428,9 +486,9 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
 //     slot lookups of a thread are issued before the first is consumed; ranks inside a warp come from
 //     ballots (0/1 matches) or a shuffle scan (duplicate build keys);
 //   * one cursor atomic and two barriers per tile; output stores of a warp step are consecutive ints.
-constexpr int kP2Threads = 256;
+constexpr int kP2Threads = 512;
 constexpr int kP2Warps = kP2Threads / 32;
-constexpr int kP2Rows = 8;
+constexpr int kP2Rows = 4;
 constexpr int kP2Tile = kP2Threads * kP2Rows;
 constexpr int kP2Stages = 3;
 
@@ -445,6 +503,12 @@ struct Probe2Smem {
   unsigned tile[kP2Stages];
   unsigned warp_tot[2][kP2Warps];
   unsigned long long tile_out[2];
+  unsigned long long part_off[kMaxParts];  // copies of Tables::offset / mask: the probe loop must not pay
+  unsigned part_mask[kMaxParts];           // an extra L2 round trip per round to fetch them
+  // per-warp straggler queue (UNIQUE path): rows whose first bucket held neither their key nor an EMPTY slot
+  unsigned long long q_key[kP2Warps][32 * kP2Rows];  // key; after resolution: output rank (or ~0 = no output)
+  unsigned q_where[kP2Warps][32 * kP2Rows];          // partition << 24 | slot; after resolution: build row
+  int32_t q_prow[kP2Warps][32 * kP2Rows];
 };
 template <typename KT>
 constexpr size_t probe2_smem_bytes() {
@@ -454,6 +518,11 @@ constexpr size_t probe2_smem_bytes() {
 static __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+static __device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 static __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -472,6 +541,22 @@ static __device__ __forceinline__ Slot ld_slot_hint(const Slot* p, uint64_t poli
   s.pad = 0;
   return s;
 }
+struct Bucket2 {  // two adjacent slots = one 32-byte sector
+  unsigned long long k0, k1;
+  int32_t r0, r1;
+};
+static __device__ __forceinline__ Bucket2 ld_bucket_hint(const Slot* p, uint64_t policy) {
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+               : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+               : "l"(p), "l"(policy));
+  Bucket2 r;
+  r.k0 = a;
+  r.r0 = (int32_t)(unsigned)b;
+  r.k1 = c;
+  r.r1 = (int32_t)(unsigned)d;
+  return r;
+}
 static __device__ __forceinline__ void st_i32_hint(int32_t* p, int32_t v, uint64_t policy) {
   asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
 }
@@ -485,17 +570,19 @@ static __device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void
 }
 
 template <typename KT, bool LEFT_LIKE, bool UNIQUE, bool WRITE>
-__global__ void __launch_bounds__(kP2Threads, 3)
+__global__ void __launch_bounds__(kP2Threads, 2)
 part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables t, int32_t* __restrict__ out_probe,
                          int32_t* __restrict__ out_build, unsigned long long* __restrict__ cursor,
-                         unsigned* __restrict__ ticket) {
+                         unsigned* __restrict__ ticket, int hint_mode) {
   using G = Probe2Geom<KT>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  Probe2Smem& sm = *reinterpret_cast<Probe2Smem*>(ring + (size_t)kP2Stages * G::kStageBytes);
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // indexed directly so that ptxas emits LDS/STS
+  unsigned char* const ring = smem_raw;
+  Probe2Smem& sm = *reinterpret_cast<Probe2Smem*>(smem_raw + (size_t)kP2Stages * G::kStageBytes);
   const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   const size_t tiles = (pr.n + kP2Tile - 1) / kP2Tile;
-  const uint64_t pol_stream = l2_policy_evict_first(), pol_table = l2_policy_evict_last();
+  // hint_mode bit 0: streams evict_first, bit 1: tables evict_last bit 2: L2 prefetch of the next tile's buckets (lab knob B200_PROBE_HINTS, default 7)
+  const uint64_t pol_stream = (hint_mode & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+  const uint64_t pol_table = (hint_mode & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
 
   auto issue = [&](int s) {
     const unsigned tl = atomicAdd(ticket, 1u);
@@ -514,6 +601,10 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
 #pragma unroll
     for (int s = 0; s < kP2Stages; ++s) issue(s);
   }
+  for (unsigned p = tid; p < g.nparts; p += kP2Threads) {
+    sm.part_off[p] = t.offset[p];
+    sm.part_mask[p] = t.mask[p];
+  }
   __syncthreads();
 
   for (unsigned iter = 0;; ++iter) {
@@ -524,9 +615,29 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
     const bool full = tile_row0 + kP2Tile <= pr.n;
     unsigned long long key[kP2Rows];
     int32_t prow[kP2Rows], first[kP2Rows];
-    unsigned cnt[kP2Rows], where[kP2Rows];  // where = partition id << 24 | first slot (slots <= 2^24 per table)
+    unsigned cnt[kP2Rows], where[kP2Rows];  // where = partition id << 24 | current slot (slots <= 2^24 per table)
+    unsigned home[UNIQUE ? 1 : kP2Rows];    // first slot of the row's probe sequence (multi-match write pass)
     bool lookup[kP2Rows];
     if (full) tma::mbar_wait(&sm.bar[s], (iter / kP2Stages) & 1u);
+    if (hint_mode & 4) {
+      // Software pipelining of the table misses: the NEXT tile's keys are already in the ring, so its
+      // first buckets are prefetched into L2 now (fire and forget) and are L2 hits one tile later.
+      // ~13 % of the look-ups are compulsory DRAM misses (every table sector is read once per ~8
+      // probes); without this a round of 2048 look-ups always waits for its slowest DRAM miss.
+      const int s1 = (int)((iter + 1) % kP2Stages);
+      const unsigned tn = sm.tile[s1];
+      if ((size_t)tn < tiles && ((size_t)tn + 1) * kP2Tile <= pr.n) {
+        tma::mbar_wait(&sm.bar[s1], ((iter + 1) / kP2Stages) & 1u);
+        const KT* nkeys = reinterpret_cast<const KT*>(ring + (size_t)s1 * G::kStageBytes);
+#pragma unroll
+        for (int i = 0; i < kP2Rows; ++i) {
+          const uint32_t h = KeyBits<KT>::hash(nkeys[warp * (32 * kP2Rows) + i * 32 + lane]);
+          const unsigned p = g.pid(h);
+          const Slot* a = t.slots + sm.part_off[p] + (slot_hash(h) & sm.part_mask[p]);
+          asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a));
+        }
+      }
+    }
     const KT* skeys = reinterpret_cast<const KT*>(ring + (size_t)s * G::kStageBytes);
     const int32_t* stags = reinterpret_cast<const int32_t*>(ring + (size_t)s * G::kStageBytes + G::kKeyBytes);
 #pragma unroll
@@ -551,35 +662,122 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
       lookup[i] = ok && key[i] != kEmptyKey;
       const uint32_t h = KeyBits<KT>::hash(kraw);
       const unsigned p = g.pid(h);
-      where[i] = (p << 24) | (slot_hash(h) & t.mask[p]);
+      where[i] = (p << 24) | (slot_hash(h) & sm.part_mask[p]);
+      if (!UNIQUE) home[i] = where[i];
     }
-    Slot s0[kP2Rows];
-#pragma unroll
-    for (int i = 0; i < kP2Rows; ++i)
-      if (lookup[i]) s0[i] = ld_slot_hint(t.slots + t.offset[where[i] >> 24] + (where[i] & 0xffffffu), pol_table);
+    // Resolve in ROUNDS: all pending look-ups of the thread are in flight together, then examined;
+    // rows whose slot held another key advance one slot and go again.  Round 0 settles ~80 % of the
+    // rows, and the number of rounds is the longest probe sequence among the warp's 256 rows, paid once
+    // per tile (resolving row by row paid max-over-32-lanes per ROW: 26 dependent L2 round trips per
+    // tile in the first version of this kernel, profiles/r01b).
+    Bucket2 cur[kP2Rows];
+    unsigned pend = 0;
 #pragma unroll
     for (int i = 0; i < kP2Rows; ++i) {
-      if (!lookup[i]) continue;
-      unsigned c = 0;
-      Slot cur = s0[i];
-      if (cur.key == key[i] && UNIQUE) {  // common case: first slot, no chain
-        first[i] = cur.row;
-        cnt[i] = 1;
-        continue;
+      if (lookup[i]) {
+        pend |= 1u << i;
+        cur[i] = ld_bucket_hint(t.slots + sm.part_off[where[i] >> 24] + (where[i] & 0xffffffu), pol_table);
       }
-      const Slot* tb = t.slots + t.offset[where[i] >> 24];
-      const unsigned m = t.mask[where[i] >> 24];
-      unsigned at = where[i] & 0xffffffu;
-      while (cur.key != kEmptyKey) {
-        if (cur.key == key[i]) {
-          if (c == 0) first[i] = cur.row;
-          ++c;
-          if (UNIQUE) break;
+    }
+    unsigned qn = 0, q_emitted = 0;  // warp-uniform: queued stragglers / how many of them produce a pair
+    if (UNIQUE) {
+      // One look at the first bucket settles ~93 % of the rows.  The rest are compacted into the
+      // warp's queue and resolved one per LANE (a lane walks its own straggler's probe sequence), so
+      // the long tail of linear probing is paid once per tile by a few lanes instead of once per row
+      // by the whole warp.
+#pragma unroll
+      for (int i = 0; i < kP2Rows; ++i) {
+        bool pending = false;
+        if ((pend >> i) & 1u) {
+          if (cur[i].k0 == key[i]) { first[i] = cur[i].r0; cnt[i] = 1; }
+          else if (cur[i].k0 == kEmptyKey) {}
+          else if (cur[i].k1 == key[i]) { first[i] = cur[i].r1; cnt[i] = 1; }
+          else if (cur[i].k1 == kEmptyKey) {}
+          else pending = true;
         }
-        at = (at + 1) & m;
-        cur = ld_slot_hint(tb + at, pol_table);
+        const unsigned bq = __ballot_sync(0xffffffffu, pending);
+        if (bq) {
+          if (pending) {
+            const unsigned e = qn + __popc(bq & lanemask_lt());
+            sm.q_key[warp][e] = key[i];
+            sm.q_where[warp][e] = where[i];
+            sm.q_prow[warp][e] = prow[i];
+            cnt[i] = 0;  // the queue entry produces this row's output
+          }
+          qn += __popc(bq);
+        }
       }
-      if (c) cnt[i] = c;
+      pend = 0;
+      __syncwarp();
+      for (unsigned base = 0; base < qn; base += 32) {
+        const unsigned e = base + lane;
+        bool emit_it = false;
+        if (e < qn) {
+          const unsigned long long k = sm.q_key[warp][e];
+          const unsigned w = sm.q_where[warp][e];
+          const Slot* tb = t.slots + sm.part_off[w >> 24];
+          const unsigned m = sm.part_mask[w >> 24];
+          unsigned at = w & 0xffffffu;
+          int32_t found = -1;
+          while (true) {
+            at = (at + 2u) & m;
+            const Bucket2 c = ld_bucket_hint(tb + at, pol_table);
+            if (c.k0 == k) { found = c.r0; break; }
+            if (c.k0 == kEmptyKey) break;
+            if (c.k1 == k) { found = c.r1; break; }
+            if (c.k1 == kEmptyKey) break;
+          }
+          emit_it = LEFT_LIKE || found >= 0;
+          sm.q_where[warp][e] = (unsigned)found;
+        }
+        const unsigned be = __ballot_sync(0xffffffffu, emit_it);
+        if (e < qn) sm.q_key[warp][e] = emit_it ? (unsigned long long)(q_emitted + __popc(be & lanemask_lt())) : ~0ull;
+        q_emitted += __popc(be);
+      }
+    }
+    while (true) {
+      // rows still pending in ANY lane (warp-uniform): later rounds touch only those, so a round costs
+      // what its stragglers cost instead of a full pass over the 8 rows
+      const unsigned any_check = __reduce_or_sync(0xffffffffu, pend);
+      if (any_check == 0) break;
+#pragma unroll
+      for (int i = 0; i < kP2Rows; ++i) {
+        if (!((any_check >> i) & 1u)) continue;
+        if (!((pend >> i) & 1u)) continue;
+        bool stop = false;
+        if (cur[i].k0 == key[i]) {
+          if (UNIQUE || first[i] < 0) first[i] = cur[i].r0;
+          if (UNIQUE) { cnt[i] = 1; stop = true; }
+          else cnt[i] = (cnt[i] & 0x80000000u) ? cnt[i] + 1 : 0x80000001u;  // bit 31: "matched at least once"
+        } else if (cur[i].k0 == kEmptyKey) {
+          stop = true;
+        }
+        if (!stop) {
+          if (cur[i].k1 == key[i]) {
+            if (UNIQUE || first[i] < 0) first[i] = cur[i].r1;
+            if (UNIQUE) { cnt[i] = 1; stop = true; }
+            else cnt[i] = (cnt[i] & 0x80000000u) ? cnt[i] + 1 : 0x80000001u;
+          } else if (cur[i].k1 == kEmptyKey) {
+            stop = true;
+          }
+        }
+        if (stop) pend &= ~(1u << i);
+      }
+      const unsigned any_issue = __reduce_or_sync(0xffffffffu, pend);
+#pragma unroll
+      for (int i = 0; i < kP2Rows; ++i) {
+        if (!((any_issue >> i) & 1u)) continue;
+        if (!((pend >> i) & 1u)) continue;
+        const unsigned p = where[i] >> 24;
+        const unsigned at = ((where[i] & 0xffffffu) + 2u) & sm.part_mask[p];
+        where[i] = (p << 24) | at;
+        cur[i] = ld_bucket_hint(t.slots + sm.part_off[p] + at, pol_table);
+      }
+    }
+    if (!UNIQUE) {
+#pragma unroll
+      for (int i = 0; i < kP2Rows; ++i)
+        if (cnt[i] & 0x80000000u) cnt[i] &= 0x7fffffffu;  // number of matches (replaces LEFT's provisional 1)
     }
     // ranks: step-major inside the warp, then warps, then the tile's reservation
     unsigned rank[kP2Rows], warp_total = 0;
@@ -600,6 +798,8 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
         warp_total += __shfl_sync(0xffffffffu, inc, 31);
       }
     }
+    const unsigned regular_total = warp_total;
+    warp_total += q_emitted;
     const unsigned buf = iter & 1u;
     if (lane == 0) sm.warp_tot[buf][warp] = warp_total;
     __syncthreads();  // stage s is consumed; warp totals visible
@@ -621,20 +821,31 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
         st_i32_hint(out_probe + pos, prow[i], pol_stream);
         st_i32_hint(out_build + pos, first[i], pol_stream);
       } else if (cnt[i] > 1) {
-        const Slot* tb = t.slots + t.offset[where[i] >> 24];
-        const unsigned m = t.mask[where[i] >> 24];
-        unsigned at = where[i] & 0xffffffu;
-        Slot cur = ld_slot_hint(tb + at, pol_table);
-        while (cur.key != kEmptyKey) {
-          if (cur.key == key[i]) {
+        const unsigned hw = home[UNIQUE ? 0 : i];
+        const Slot* tb = t.slots + sm.part_off[hw >> 24];
+        const unsigned m = sm.part_mask[hw >> 24];
+        unsigned at = hw & 0xffffffu;
+        Slot c2 = ld_slot_hint(tb + at, pol_table);
+        while (c2.key != kEmptyKey) {
+          if (c2.key == key[i]) {
             out_probe[pos] = prow[i];
-            out_build[pos] = cur.row;
+            out_build[pos] = c2.row;
             ++pos;
           }
           at = (at + 1) & m;
-          cur = ld_slot_hint(tb + at, pol_table);
+          c2 = ld_slot_hint(tb + at, pol_table);
         }
       }
+    }
+    if (UNIQUE) {  // the warp's stragglers follow its regular rows
+      for (unsigned e = lane; e < qn; e += 32) {
+        const unsigned long long r = sm.q_key[warp][e];
+        if (r == ~0ull) continue;
+        const size_t pos = pos0 + regular_total + (size_t)r;
+        st_i32_hint(out_probe + pos, sm.q_prow[warp][e], pol_stream);
+        st_i32_hint(out_build + pos, (int32_t)sm.q_where[warp][e], pol_stream);
+      }
+      __syncwarp();  // the queue is rewritten by the next tile
     }
   }
 }
@@ -705,10 +916,13 @@ gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, S
   B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
   B200_CUDA_TRY(keys_out.alloc((run ? run : 1) * sizeof(KT)));
   B200_CUDA_TRY(rows_out.alloc((run ? run : 1) * sizeof(int32_t)));
-  auto kern = part_scatter_kernel<KT, KEEP_NULLS>;
+  static const bool prefetch = getenv("B200_SCATTER_PREFETCH") ? atoi(getenv("B200_SCATTER_PREFETCH")) != 0 : true;
+  auto kern = prefetch ? part_scatter_kernel<KT, KEEP_NULLS, true> : part_scatter_kernel<KT, KEEP_NULLS, false>;
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<KT>)));
+  int per_sm = 1;
+  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, sizeof(ScatterSmem<KT>)));
   const size_t tiles = (n + kScatterTile - 1) / kScatterTile;
-  const size_t cap = (size_t)sm_count() * 3;
+  const size_t cap = (size_t)sm_count() * (size_t)(per_sm > 0 ? per_sm : 1);  // exactly one resident wave
   const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
   {
     B200_TIMED("join_part_scatter");
@@ -736,9 +950,10 @@ gdf_error launch_probe_stream(const Pairs<KT>& pr, PartGeom g, const Tables& t, 
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), 0));
   const size_t tiles = (pr.n + kP2Tile - 1) / kP2Tile;
-  const size_t resident = (size_t)sm_count() * (sizeof(KT) == 8 ? 3 : 4);
+  const size_t resident = (size_t)sm_count() * 2;
   const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
-  kern<<<blocks, kP2Threads, smem>>>(pr, g, t, op, ob, cursor, ticket);
+  static const int hint_mode = getenv("B200_PROBE_HINTS") ? atoi(getenv("B200_PROBE_HINTS")) : 7;
+  kern<<<blocks, kP2Threads, smem>>>(pr, g, t, op, ob, cursor, ticket, hint_mode);
   B200_CHECK_LAST();
   return GDF_SUCCESS;
 }
@@ -748,7 +963,8 @@ gdf_error launch_probe(bool unique, bool write, const Pairs<KT>& pr, PartGeom g,
                        int32_t* ob, unsigned long long* cursor, unsigned* ticket, bool stream_ok) {
   if (pr.n == 0) return GDF_SUCCESS;
   B200_TIMED(write ? "join_part_probe" : "join_part_count");
-  if (pr.rows != nullptr && stream_ok) {  // partitioned {key,tag} pairs: streaming kernel
+  static const bool force_v1 = getenv("B200_PROBE_V1") ? atoi(getenv("B200_PROBE_V1")) != 0 : true;  // lab knob; the one-tile-per-CTA kernel is the fastest measured so far (profiles/r01b)
+  if (pr.rows != nullptr && stream_ok && !force_v1) {  // partitioned {key,tag} pairs: streaming kernel
     if (unique) {
       if (write) return launch_probe_stream<KT, LEFT_LIKE, true, true>(pr, g, t, op, ob, cursor, ticket);
       return launch_probe_stream<KT, LEFT_LIKE, true, false>(pr, g, t, op, ob, cursor, ticket);

@@ -1,21 +1,22 @@
-// Streaming select (v2) for ONE aligned column: persistent CTAs, TMA-staged tiles, wide look-back.
+// Streaming select (v3) for ONE aligned column: persistent CTAs, TMA-staged tiles, CHUNKED look-back.
 //
-// Why a second kernel (profiles/r01a_ncu_full_summary.md, select_kernel): with one tile per CTA and
-// a 32-descriptor look-back window the kernel ran at 2.7 TB/s with 24 warps-per-issue stalled on the
-// CTA barrier: ~450 tiles are in flight on 148 SMs, every tile has to walk back over the aggregates
-// of the other in-flight tiles 32 at a time (one L2 round trip each), and nothing is loading while a
-// CTA waits.  Here:
-//   * CTAs are persistent and take tiles from a global ticket counter (so a tile's predecessors are
-//     always held by running CTAs); tiles are 32 KB and arrive through a 3-stage shared-memory ring
-//     filled by cp.async.bulk (stream.cuh) - the next two tiles are in flight while the current one
-//     is ranked, looked back and written;
-//   * the look-back reads 256 descriptors per round trip (8 per lane of warp 0), so one round
-//     normally covers every in-flight tile;
-//   * each thread owns R CONSECUTIVE rows of the tile (read from shared memory with an XOR swizzle
-//     so that the 128-bit reads are bank-conflict free), which makes the output rank a plain
-//     popc + warp scan instead of R ballots.
-// Output order is ascending row order, exactly like the first kernel (and like thrust::copy_if in
-// the reference, sqls_rtti_comp.hpp:358-365).
+// History (profiles/): v1 (select.cuh, one 32 KB tile per CTA, 32-descriptor look-back) ran C2 at
+// 2.7 TB/s with 24 warps-per-issue stalled on the CTA barrier.  The cause is structural: a tile cannot
+// be written before the running total of ALL earlier tiles is known, and that total travels through
+// L2 one look-back hop (~1 us under load) at a time.  A hop that covers 32 tiles of 32 KB moves the
+// prefix 1 MB per microsecond - 1 TB/s.  v2 kept the per-tile protocol (persistent CTAs, 256-wide
+// hops) and measured even worse (10 ms): with ~300 CTAs in lock step every iteration still waits
+// for three serial hops.  v3 changes the granularity of the chain instead:
+//   * a CTA processes CHUNKS of 16 consecutive tiles (64 K int64 rows, 512 KB).  Pass 1 streams the
+//     16 tiles through a 3-stage cp.async.bulk ring (stream.cuh), and every thread keeps the predicate
+//     bits of its rows - 16 consecutive rows per tile - in registers (the output of gdf_filter is the
+//     row INDEX, so the data is not needed again);
+//   * ONE descriptor per chunk is published and ONE look-back per chunk is done (a hop now moves the
+//     prefix 256 x 512 KB); the next chunk's first tiles are already in flight while warp 0 waits;
+//   * pass 2 ranks the kept bits (warp scan per tile done in pass 1, one pass over the 16 x 8 warp
+//     totals) and writes the indices, ascending.
+// Output order is ascending row order (stable), like thrust::copy_if in the reference
+// (sqls_rtti_comp.hpp:358-365).
 #pragma once
 #include "select.cuh"
 #include "stream.cuh"
@@ -26,46 +27,48 @@ namespace select_stream {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStages = 3;
+constexpr int kChunkTiles = 16;
 
 template <typename T>
 struct Geom {
-  static constexpr int R = sizeof(T) == 8 ? 16 : 32;          // rows per thread (flags fit 32 bits)
+  static constexpr int R = sizeof(T) == 8 ? 16 : 32;          // rows per thread per tile (flags fit 32 bits)
   static constexpr int kTileRows = kThreads * R;
   static constexpr int kTileBytes = kTileRows * (int)sizeof(T);  // 32 KB for 8- and 4-byte types
+  static constexpr int kChunkRows = kTileRows * kChunkTiles;
   static constexpr int C = R * (int)sizeof(T) / 16;            // 16-byte chunks per thread
-  static constexpr int E = 16 / (int)sizeof(T);                // elements per chunk
+  static constexpr int E = 16 / (int)sizeof(T);                // elements per 16-byte chunk
 };
 
 struct Smem {
   uint64_t bar[kStages];
-  unsigned tile[kStages];
-  uint32_t warp_tot[2][kWarps];
-  uint64_t tile_excl[2];
+  uint32_t warp_tot[kChunkTiles][kWarps];
+  uint64_t chunk_excl;
 };
 
 template <typename T>
 constexpr size_t smem_bytes() {
-  return (size_t)kStages * Geom<T>::kTileBytes + sizeof(Smem) + 128;
+  return (size_t)kStages * Geom<T>::kTileBytes + sizeof(Smem);
 }
 
-// Publishes this tile's total and returns the exclusive prefix of all earlier tiles; runs in warp 0.
-static __device__ __forceinline__ uint64_t lookback_wide(uint64_t* desc, unsigned tile, uint64_t total) {
+// Publishes this chunk's total and returns the exclusive prefix of all earlier chunks; runs in warp 0.
+// 256 descriptors (8 per lane) are read per round trip.
+static __device__ __forceinline__ uint64_t lookback_wide(uint64_t* desc, unsigned idx0, uint64_t total) {
   using namespace select_detail;
   const unsigned lane = lane_id();
-  if (tile == 0) {
+  if (idx0 == 0) {
     if (lane == 0) st_desc(desc, kPrefix | total);
     return 0;
   }
-  if (lane == 0) st_desc(desc + tile, kAgg | total);
+  if (lane == 0) st_desc(desc + idx0, kAgg | total);
   uint64_t acc = 0;
-  long long base = (long long)tile - 1;  // nearest predecessor
+  long long base = (long long)idx0 - 1;  // nearest predecessor
   bool done = false;
   while (!done) {
     uint64_t d[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {  // window j = 32 consecutive predecessors, nearest first
       const long long idx = base - (j * 32 + (int)lane);
-      d[j] = idx >= 0 ? ld_desc(desc + idx) : kPrefix;  // before tile 0: prefix 0
+      d[j] = idx >= 0 ? ld_desc(desc + idx) : kPrefix;  // before the first: prefix 0
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -88,99 +91,124 @@ static __device__ __forceinline__ uint64_t lookback_wide(uint64_t* desc, unsigne
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-  if (lane == 0) st_desc(desc + tile, kPrefix | (acc + total));
+  if (lane == 0) st_desc(desc + idx0, kPrefix | (acc + total));
   return acc;
 }
 
 // Pred: void prepare() (once per thread, may read device scalars); bool operator()(T) const.
 // Emit: void operator()(size_t row, size_t pos) const.
+// Chunks are dealt round-robin (CTA b: chunks b, b + grid, ...); the grid never exceeds what is
+// co-resident (occupancy API on the host), so the CTA holding a predecessor chunk is always running.
 template <typename T, typename Pred, typename Emit>
 __global__ void __launch_bounds__(kThreads)
 select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit, uint64_t* __restrict__ desc,
-                     unsigned* __restrict__ ticket, unsigned long long* __restrict__ count_out) {
+                     unsigned long long* __restrict__ count_out) {
   using G = Geom<T>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  Smem& sm = *reinterpret_cast<Smem*>(ring + (size_t)kStages * G::kTileBytes);
+  extern __shared__ __align__(16) unsigned char select_smem[];
+  unsigned char* const ring = select_smem;
+  Smem& sm = *reinterpret_cast<Smem*>(select_smem + (size_t)kStages * G::kTileBytes);
   const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   const size_t tiles = (n + G::kTileRows - 1) / G::kTileRows;
+  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
   pred.prepare();
 
-  // one thread takes a ticket for stage s and starts the copy of that tile
-  auto issue = [&](int s) {
-    const unsigned t = atomicAdd(ticket, 1u);
-    sm.tile[s] = t;
-    if ((size_t)t < tiles && ((size_t)t + 1) * G::kTileRows <= n) {
+  // The CTA's tiles form one sequence q = 0, 1, 2, ...: tile q is tile (q % 16) of chunk
+  // blockIdx.x + (q / 16) * gridDim.x and lives in ring stage q % kStages.
+  auto tile_index = [&](unsigned q) {
+    return ((size_t)blockIdx.x + (size_t)(q / kChunkTiles) * gridDim.x) * kChunkTiles + (q % kChunkTiles);
+  };
+  auto issue = [&](unsigned q) {  // one thread starts the copy of the CTA's q-th tile (full tiles only)
+    const size_t t = tile_index(q);
+    const int s = (int)(q % kStages);
+    if (t < tiles && (t + 1) * G::kTileRows <= n) {
       tma::mbar_expect_tx(&sm.bar[s], G::kTileBytes);
-      tma::bulk_load(ring + (size_t)s * G::kTileBytes, data + (size_t)t * G::kTileRows, G::kTileBytes, &sm.bar[s]);
+      tma::bulk_load(ring + (size_t)s * G::kTileBytes, data + t * G::kTileRows, G::kTileBytes, &sm.bar[s]);
     }
   };
-
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) tma::mbar_init(&sm.bar[s], 1);
     tma::fence_barrier_init();
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) issue(s);
+    for (int s = 0; s < kStages; ++s) issue((unsigned)s);
   }
   __syncthreads();
 
-  for (unsigned iter = 0;; ++iter) {
-    const int s = (int)(iter % kStages);
-    const unsigned t = sm.tile[s];
-    if ((size_t)t >= tiles) break;  // tickets only grow: nothing of this CTA is in flight any more
-    const size_t tile_row0 = (size_t)t * G::kTileRows;
-    const bool full = tile_row0 + G::kTileRows <= n;
-    uint32_t f = 0;
-    if (full) {
-      tma::mbar_wait(&sm.bar[s], (iter / kStages) & 1u);
-      const uint4* mine = reinterpret_cast<const uint4*>(ring + (size_t)s * G::kTileBytes) + (size_t)tid * G::C;
+  unsigned q = 0;                  // tiles consumed so far by this CTA
+  unsigned phase_bits = 0;         // bit s = parity the next FULL tile of stage s completes
+  for (size_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+    uint32_t f[kChunkTiles], excl[kChunkTiles];
 #pragma unroll
-      for (int j = 0; j < G::C; ++j) {
-        const int c = j ^ (int)(lane & (G::C - 1));  // swizzle: a quarter-warp touches 8 different bank groups
-        const uint4 raw = mine[c];
-        const T* e = reinterpret_cast<const T*>(&raw);
+    for (int k = 0; k < kChunkTiles; ++k, ++q) {
+      const size_t t = chunk * kChunkTiles + k;
+      const size_t tile_row0 = t * G::kTileRows;
+      const int s = (int)(q % kStages);
+      uint32_t bits = 0;
+      if (tile_row0 + G::kTileRows <= n) {  // full tile: staged by TMA
+        tma::mbar_wait(&sm.bar[s], (phase_bits >> s) & 1u);
+        phase_bits ^= 1u << s;
+        const uint4* mine = reinterpret_cast<const uint4*>(ring + (size_t)s * G::kTileBytes) + (size_t)tid * G::C;
 #pragma unroll
-        for (int k = 0; k < G::E; ++k) f |= (uint32_t)pred(e[k]) << (c * G::E + k);
-      }
-    } else {  // ragged last tile: direct loads
-      const size_t row0 = tile_row0 + (size_t)tid * G::R;
+        for (int j = 0; j < G::C; ++j) {
+          const int c = j ^ (int)(lane & (G::C - 1));  // swizzle: a quarter-warp touches 8 different bank groups
+          const uint4 raw = mine[c];
+          const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+          for (int i = 0; i < G::E; ++i) bits |= (uint32_t)pred(e[i]) << (c * G::E + i);
+        }
+      } else if (tile_row0 < n) {  // ragged last tile: direct loads
+        const size_t row0 = tile_row0 + (size_t)tid * G::R;
 #pragma unroll 4
-      for (int k = 0; k < G::R; ++k)
-        if (row0 + k < n) f |= (uint32_t)pred(data[row0 + k]) << k;
-    }
-    const uint32_t cnt = __popc(f);
-    uint32_t inc = cnt;
+        for (int i = 0; i < G::R; ++i)
+          if (row0 + i < n) bits |= (uint32_t)pred(data[row0 + i]) << i;
+      }
+      f[k] = bits;
+      uint32_t inc = __popc(bits);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= (unsigned)d) inc += o;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += o;
+      }
+      excl[k] = inc - __popc(bits);
+      if (lane == 31) sm.warp_tot[k][warp] = inc;
+      __syncthreads();  // every thread is done with stage s (and, for k = 15, all warp totals are visible)
+      if (tid == 0) issue(q + kStages);
     }
-    const unsigned buf = iter & 1u;
-    if (lane == 31) sm.warp_tot[buf][warp] = inc;
-    __syncthreads();  // every thread is done with stage s; warp totals are visible
-    if (tid == 32) issue(s);
     if (warp == 0) {
-      uint32_t tot = 0;
+      uint32_t part = 0;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) tot += sm.warp_tot[buf][w];
-      const uint64_t excl = lookback_wide(desc, t, tot);
+      for (int j = 0; j < kChunkTiles * kWarps / 32; ++j) part += (&sm.warp_tot[0][0])[j * 32 + lane];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+      const uint64_t before = lookback_wide(desc, (unsigned)chunk, part);
       if (lane == 0) {
-        sm.tile_excl[buf] = excl;
-        if ((size_t)t == tiles - 1) *count_out = excl + tot;
+        sm.chunk_excl = before;
+        if (chunk == chunks - 1) *count_out = before + part;
       }
     }
     __syncthreads();
-    if (cnt) {
-      size_t pos = sm.tile_excl[buf] + (inc - cnt);
-      for (unsigned w = 0; w < warp; ++w) pos += sm.warp_tot[buf][w];
-      const size_t row0 = tile_row0 + (size_t)tid * G::R;
-      while (f) {
-        const int k = __ffs(f) - 1;
-        f &= f - 1;
-        emit(row0 + k, pos++);
+    // pass 2: ranks in (tile, warp, lane, bit) order = ascending row order
+    size_t run = (size_t)sm.chunk_excl;
+#pragma unroll
+    for (int k = 0; k < kChunkTiles; ++k) {
+      size_t pos = run + excl[k];
+      uint32_t tile_total = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t wt = sm.warp_tot[k][w];
+        if ((unsigned)w < warp) pos += wt;
+        tile_total += wt;
+      }
+      run += tile_total;
+      uint32_t bits = f[k];
+      const size_t row0 = (chunk * kChunkTiles + k) * G::kTileRows + (size_t)tid * G::R;
+      while (bits) {
+        const int i = __ffs(bits) - 1;
+        bits &= bits - 1;
+        emit(row0 + i, pos++);
       }
     }
+    __syncthreads();  // warp_tot / chunk_excl are rewritten by the next chunk
   }
 }
 

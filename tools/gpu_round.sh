@@ -34,7 +34,7 @@ fi
 if has full; then
   # quarter-size inputs: ncu's kernel replay saves/restores every written allocation; the partition
   # geometry (rows per partition, table bytes per partition) is the same as at full size.
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'part_|select_kernel|build_fast|extract_fast' \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'part_|select_|build_fast|extract_fast' \
     -c 24 -f -o $OUT/prof_full python bench.py --scale 0.25 --steps 1 --warmup 0 --no-e2e --no-cpu > $OUT/prof_full.log 2>&1
   echo "full rc=$?"
 fi
