@@ -432,6 +432,8 @@ def bench_dist(args, rank, world, local_rank):
     one hash-partition + all-to-all + local join per step; max over ranks of the device time."""
     import torch.distributed as dist
     from libgdf_b200 import dist as D
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"      # stdout carries exactly one JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api = Api("b200")
     ops = D.GdfOps()
@@ -539,10 +541,19 @@ def bench_dist(args, rank, world, local_rank):
                "kernels_rank0": kernels, "clocks": clocks.summarise(clocks.window(t0, t1)),
                "gpu_launches": int(sum(k["launches_per_step"] for k in kernels.values()) * args.steps) if kernels else None}
         if top:
-            out["roofline"] = {"kernel": top, "bound": "hbm", "achieved": None, "peak": peak_gbs, "unit": "GB/s",
-                               "frac": None, "traffic": None, "peak_source": peak_kind,
-                               "note": "per-kernel algorithmic bytes are defined for the N=1 path (DESIGN.md); at N>1 "
-                                       "the step is bounded by the NVLink all-to-all, see phases_ms_rank0"}
+            # dominant kernel of rank 0 on its share of the rows (P/N probe pairs, B/N build pairs)
+            per_launch = {"join_part_probe": 12 * P / world + 8 * pairs / world,
+                          "join_part_scatter": (8 + 12) * (P + B) / world / 4.0,   # 4 launches: exchange + local, 2 sides
+                          "join_part_hist": 8 * (P + B) / world / 4.0,
+                          "join_part_build": (12 + 16) * B / world}.get(top)
+            ms_l = kernels[top]["ms_per_step"] / max(kernels[top]["launches_per_step"], 1)
+            ach = per_launch / 1e9 / (ms_l * 1e-3) if per_launch else None
+            out["roofline"] = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
+                               "frac": ach / peak_gbs if ach else None, "traffic": None, "peak_source": peak_kind,
+                               "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": ms_l,
+                               "note": "rank 0's dominant kernel on its 1/N share; the step as a whole is bounded by the "
+                                       "NVLink all-to-all (phases_ms_rank0), %.2f GB sent per rank per step"
+                                       % (12 * (P + B) / world * (world - 1) / world / 1e9)}
         if e2e:
             out["e2e"] = e2e
         print(json.dumps(out))

@@ -14,3 +14,17 @@ size_t gdfx_profile_report(char *buf, size_t capacity);
  * non-negative entry (< payload_rows), -1 otherwise.  `indices` is a GDF_INT32 join output column;
  * `payload` is a device array of the global row ids that travelled with the exchanged keys. */
 gdf_error gdfx_remap_indices(gdf_column *indices, const int32_t *payload, size_t payload_rows);
+
+/* Multi-GPU layer: split one 4/8-byte integer key column into num_partitions destination ranges of
+ * {key, global row id} pairs, ids = id_base + row position.  out_keys (same width as the key) and out_ids
+ * are caller-allocated device buffers of key->size elements; partition_offsets is a HOST array of
+ * num_partitions + 1 start offsets.  The destination of a key is a fixed function of its value, the same on
+ * every rank and independent of the hash bits the single-GPU join uses internally. */
+gdf_error gdfx_partition_pairs(gdf_column *key, int32_t id_base, int num_partitions, void *out_keys,
+                               int32_t *out_ids, unsigned long long *partition_offsets);
+
+/* Multi-GPU layer: gdf_inner_join (kind 0) / gdf_left_join (kind 1) on ONE key column of exchanged rows whose
+ * global row ids travel beside the keys; the GDF_INT32 output columns (library-allocated, freed with
+ * gdf_column_free) hold those ids instead of positions, -1 = no partner. */
+gdf_error gdfx_join_pairs(int kind, gdf_column *left_key, const int32_t *left_ids, gdf_column *right_key,
+                          const int32_t *right_ids, gdf_column *out_l, gdf_column *out_r);

@@ -34,7 +34,10 @@ namespace b200 {
 
 // radix-partitioned single-key path (join_part.cu)
 gdf_error partitioned_join(int kind, const gdf_column* probe_key, const gdf_column* build_key, bool flip,
-                           gdf_column* out_l, gdf_column* out_r, bool* handled);
+                           gdf_column* out_l, gdf_column* out_r, bool* handled, const int32_t* probe_payload = nullptr,
+                           const int32_t* build_payload = nullptr);
+gdf_error partition_pairs(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* out_keys,
+                          int32_t* out_ids, unsigned long long* h_offsets);
 
 namespace {
 
@@ -578,3 +581,53 @@ using namespace b200;
 B200_JOIN(inner, JOIN_INNER)
 B200_JOIN(left, JOIN_LEFT)
 B200_JOIN(full, JOIN_FULL)
+
+// ---- multi-GPU layer entry points (include/gdf_b200_ext.h); the reference has no counterpart ----
+extern "C" gdf_error gdfx_remap_indices(gdf_column* indices, const int32_t* payload, size_t payload_rows);
+
+extern "C" gdf_error gdfx_partition_pairs(gdf_column* key, int32_t id_base, int num_partitions, void* out_keys,
+                                          int32_t* out_ids, unsigned long long* partition_offsets) {
+  B200_REQUIRE(key != nullptr && out_keys != nullptr && out_ids != nullptr && partition_offsets != nullptr,
+               GDF_DATASET_EMPTY);
+  B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
+  B200_REQUIRE(num_partitions >= 1, GDF_INVALID_API_CALL);
+  B200_REQUIRE(key->size < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
+  if (key->size == 0) {
+    for (int p = 0; p <= num_partitions; ++p) partition_offsets[p] = 0;
+    return GDF_SUCCESS;
+  }
+  return partition_pairs(key, id_base, (unsigned)num_partitions, out_keys, out_ids, partition_offsets);
+}
+
+// Join of exchanged {key, global row id} pairs: like gdf_inner_join / gdf_left_join on ONE key column, but the
+// output columns hold the rows' ids (payload) instead of their positions.  kind: 0 inner, 1 left.
+extern "C" gdf_error gdfx_join_pairs(int kind, gdf_column* left_key, const int32_t* left_ids, gdf_column* right_key,
+                                     const int32_t* right_ids, gdf_column* out_l, gdf_column* out_r) {
+  B200_REQUIRE(left_key && right_key && out_l && out_r && left_ids && right_ids, GDF_DATASET_EMPTY);
+  B200_REQUIRE(kind == JOIN_INNER || kind == JOIN_LEFT, GDF_UNSUPPORTED_JOIN_TYPE);
+  B200_REQUIRE(left_key->dtype == right_key->dtype, GDF_JOIN_DTYPE_MISMATCH);
+  B200_REQUIRE(!left_key->valid && !right_key->valid, GDF_VALIDITY_UNSUPPORTED);
+  const size_t L = left_key->size, R = right_key->size;
+  B200_REQUIRE(L < 0x7fffffffull && R < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
+  gdf_column_view(out_l, nullptr, nullptr, 0, N_GDF_TYPES);
+  gdf_column_view(out_r, nullptr, nullptr, 0, N_GDF_TYPES);
+  if (L == 0 || (kind == JOIN_INNER && R == 0)) return GDF_SUCCESS;
+  const bool flip = kind == JOIN_INNER && R > L;
+  gdf_column* probe = flip ? right_key : left_key;
+  gdf_column* build = flip ? left_key : right_key;
+  bool handled = false;
+  gdf_error e = partitioned_join(kind, probe, build, flip, out_l, out_r, &handled, flip ? right_ids : left_ids,
+                                 flip ? left_ids : right_ids);
+  if (e != GDF_SUCCESS || handled) return e;
+  // key types / inputs the partitioned path does not take: generic join on positions, then map to ids
+  gdf_column* pc[1] = {probe};
+  gdf_column* bc[1] = {build};
+  TableView pv, bv;
+  make_view(pv, pc, 1);
+  make_view(bv, bc, 1);
+  e = generic_hash_join(kind, pv, bv, flip, out_l, out_r);
+  if (e != GDF_SUCCESS) return e;
+  e = gdfx_remap_indices(out_l, left_ids, L);
+  if (e == GDF_SUCCESS) e = gdfx_remap_indices(out_r, right_ids, R);
+  return e;
+}

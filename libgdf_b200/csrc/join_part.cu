@@ -78,9 +78,14 @@ template <> struct KeyBits<uint32_t> {
 static __device__ __forceinline__ uint32_t slot_hash(uint32_t h) { return ((h * 0x9E3779B1u) >> 7) & ~1u; }
 
 struct PartGeom {
-  unsigned nparts;  // power of two
+  unsigned nparts;  // power of two (local radix partitions) or any count (dest mode)
   unsigned shift;   // pid = hash >> shift   (shift = 32 - log2(nparts)); nparts == 1 -> pid = 0
-  __device__ __forceinline__ unsigned pid(uint32_t h) const { return nparts == 1 ? 0u : (h >> shift); }
+  unsigned dest;    // 1 = "destination rank" mode of the multi-GPU layer: pid = mulhi(remix(hash), nparts), a
+                    // function that is independent of the top bits the receiver's local partitioning uses
+  __device__ __forceinline__ unsigned pid(uint32_t h) const {
+    if (dest) return __umulhi(fmix32(h ^ 0x5bd1e995u), nparts);
+    return nparts == 1 ? 0u : (h >> shift);
+  }
 };
 
 // ---- pass 1: per-partition row counts.  Shared-memory 32-bit atomics are the cheapest primitive on
@@ -165,7 +170,7 @@ template <typename KT, bool KEEP_NULLS, bool PREFETCH>
 __global__ void __launch_bounds__(kThreads, PREFETCH ? 2 : 3)
 part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
                     unsigned long long* __restrict__ cursors, KT* __restrict__ out_keys,
-                    int32_t* __restrict__ out_rows) {
+                    int32_t* __restrict__ out_rows, const int32_t* __restrict__ payload, int32_t id_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem<KT>& sm = *reinterpret_cast<ScatterSmem<KT>*>(smem_raw);
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -241,7 +246,9 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
       if ((rp[i] & 0xffffu) == 0xffffu) continue;
       const unsigned p = rp[i] & 0x7fffu;
       const unsigned at = sm.lstart[p] + (rp[i] >> 16);
-      const int32_t r = (int32_t)(wbase + (size_t)i * 32 + lane);
+      const size_t row = wbase + (size_t)i * 32 + lane;
+      // row tag: position in the column, or the caller's payload (global row id of an exchanged row)
+      const int32_t r = payload ? payload[row] : (int32_t)row + id_base;
       sm.keys[at] = k[i];
       sm.rows[at] = (rp[i] & 0x8000u) ? ~r : r;
       sm.pid[at] = (unsigned short)p;
@@ -896,7 +903,8 @@ unsigned pow2_at_least(size_t x) {
 template <typename KT, bool KEEP_NULLS>
 gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, Scratch& rows_out,
                          unsigned long long* d_totals /*device [nparts]*/, unsigned long long* d_cursors,
-                         unsigned long long* h_totals, size_t* kept) {
+                         unsigned long long* h_totals, size_t* kept, const int32_t* payload = nullptr,
+                         int32_t id_base = 0, KT* ext_keys = nullptr, int32_t* ext_rows = nullptr) {
   const KT* keys = static_cast<const KT*>(col->data);
   const size_t n = col->size;
   B200_CUDA_TRY(cudaMemsetAsync(d_totals, 0, g.nparts * sizeof(unsigned long long), 0));
@@ -914,8 +922,12 @@ gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, S
   }
   *kept = (size_t)run;
   B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  B200_CUDA_TRY(keys_out.alloc((run ? run : 1) * sizeof(KT)));
-  B200_CUDA_TRY(rows_out.alloc((run ? run : 1) * sizeof(int32_t)));
+  if (!ext_keys) {
+    B200_CUDA_TRY(keys_out.alloc((run ? run : 1) * sizeof(KT)));
+    B200_CUDA_TRY(rows_out.alloc((run ? run : 1) * sizeof(int32_t)));
+    ext_keys = keys_out.as<KT>();
+    ext_rows = rows_out.as<int32_t>();
+  }
   static const bool prefetch = getenv("B200_SCATTER_PREFETCH") ? atoi(getenv("B200_SCATTER_PREFETCH")) != 0 : true;
   auto kern = prefetch ? part_scatter_kernel<KT, KEEP_NULLS, true> : part_scatter_kernel<KT, KEEP_NULLS, false>;
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<KT>)));
@@ -926,8 +938,8 @@ gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, S
   const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
   {
     B200_TIMED("join_part_scatter");
-    kern<<<sblocks, kThreads, sizeof(ScatterSmem<KT>)>>>(keys, col->valid, n, g, d_cursors, keys_out.as<KT>(),
-                                                        rows_out.as<int32_t>());
+    kern<<<sblocks, kThreads, sizeof(ScatterSmem<KT>)>>>(keys, col->valid, n, g, d_cursors, ext_keys, ext_rows, payload,
+                                                        id_base);
   }
   B200_CHECK_LAST();
   return GDF_SUCCESS;
@@ -991,10 +1003,12 @@ void view_indices(gdf_column* c, int32_t* data, size_t n) {
 
 template <typename KT>
 gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_column* build_col, bool flip,
-                          gdf_column* out_l, gdf_column* out_r, bool* handled) {
+                          gdf_column* out_l, gdf_column* out_r, bool* handled, const int32_t* probe_payload,
+                          const int32_t* build_payload) {
   const size_t P = probe_col->size, B = build_col->size;
   const bool left_like = kind != JOIN_INNER;
   PartGeom g;
+  g.dest = 0;
   {
     unsigned np = pow2_at_least((B + kRowsPerPartition - 1) / kRowsPerPartition);
     if (np > kMaxParts) np = kMaxParts;
@@ -1016,17 +1030,18 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 4 * sizeof(unsigned long long), 0));
 
   Scratch bkeys, brows, pkeys, prows;
-  Pairs<KT> bp{static_cast<const KT*>(build_col->data), nullptr, build_col->valid, B};
-  Pairs<KT> pp{static_cast<const KT*>(probe_col->data), nullptr, probe_col->valid, P};
+  // unpartitioned pairs: row tag = position, or the caller's payload (then masks are not supported)
+  Pairs<KT> bp{static_cast<const KT*>(build_col->data), build_payload, build_col->valid, B};
+  Pairs<KT> pp{static_cast<const KT*>(probe_col->data), probe_payload, probe_col->valid, P};
   unsigned long long h_btot[kMaxParts];
   if (g.nparts > 1) {
     unsigned long long h_ptot[kMaxParts];
     size_t kept = 0;
-    gdf_error e = partition_side<KT, false>(build_col, g, bkeys, brows, d_totals, d_cursors, h_btot, &kept);
+    gdf_error e = partition_side<KT, false>(build_col, g, bkeys, brows, d_totals, d_cursors, h_btot, &kept, build_payload);
     if (e != GDF_SUCCESS) return e;
     bp = Pairs<KT>{bkeys.as<KT>(), brows.as<int32_t>(), nullptr, kept};
-    e = left_like ? partition_side<KT, true>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept)
-                  : partition_side<KT, false>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept);
+    e = left_like ? partition_side<KT, true>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept, probe_payload)
+                  : partition_side<KT, false>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept, probe_payload);
     if (e != GDF_SUCCESS) return e;
     pp = Pairs<KT>{pkeys.as<KT>(), prows.as<int32_t>(), nullptr, kept};
   } else {
@@ -1123,14 +1138,53 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
 }  // namespace
 
 gdf_error partitioned_join(int kind, const gdf_column* probe_key, const gdf_column* build_key, bool flip,
-                           gdf_column* out_l, gdf_column* out_r, bool* handled) {
+                           gdf_column* out_l, gdf_column* out_r, bool* handled, const int32_t* probe_payload,
+                           const int32_t* build_payload) {
   *handled = false;
   switch (probe_key->dtype) {
     case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
-      return run_partitioned<uint64_t>(kind, probe_key, build_key, flip, out_l, out_r, handled);
+      return run_partitioned<uint64_t>(kind, probe_key, build_key, flip, out_l, out_r, handled, probe_payload, build_payload);
     case GDF_INT32: case GDF_DATE32:
-      return run_partitioned<uint32_t>(kind, probe_key, build_key, flip, out_l, out_r, handled);
+      return run_partitioned<uint32_t>(kind, probe_key, build_key, flip, out_l, out_r, handled, probe_payload, build_payload);
     default: return GDF_SUCCESS;  // floats / narrow ints: generic path
+  }
+}
+
+// Multi-GPU layer: split one key column into `num_partitions` destination ranges of {key, global row id}
+// pairs (ids = id_base + position).  h_offsets receives num_partitions + 1 start offsets (host).
+template <typename KT>
+gdf_error partition_pairs_typed(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* out_keys,
+                                int32_t* out_ids, unsigned long long* h_offsets) {
+  PartGeom g;
+  g.nparts = num_partitions;
+  g.shift = 0;
+  g.dest = 1;
+  Scratch small, unused_a, unused_b;
+  B200_CUDA_TRY(small.alloc(2 * (size_t)num_partitions * sizeof(unsigned long long)));
+  unsigned long long h_tot[kMaxParts];
+  size_t kept = 0;
+  gdf_error e = partition_side<KT, false>(key, g, unused_a, unused_b, small.as<unsigned long long>(),
+                                          small.as<unsigned long long>() + num_partitions, h_tot, &kept, nullptr, id_base,
+                                          static_cast<KT*>(out_keys), out_ids);
+  if (e != GDF_SUCCESS) return e;
+  unsigned long long run = 0;
+  for (unsigned p = 0; p < num_partitions; ++p) {
+    h_offsets[p] = run;
+    run += h_tot[p];
+  }
+  h_offsets[num_partitions] = run;
+  return GDF_SUCCESS;
+}
+
+gdf_error partition_pairs(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* out_keys,
+                          int32_t* out_ids, unsigned long long* h_offsets) {
+  B200_REQUIRE(num_partitions >= 1 && num_partitions <= kMaxParts, GDF_INVALID_API_CALL);
+  switch (key->dtype) {
+    case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
+      return partition_pairs_typed<uint64_t>(key, id_base, num_partitions, out_keys, out_ids, h_offsets);
+    case GDF_INT32: case GDF_DATE32:
+      return partition_pairs_typed<uint32_t>(key, id_base, num_partitions, out_keys, out_ids, h_offsets);
+    default: return GDF_UNSUPPORTED_DTYPE;
   }
 }
 

@@ -6,12 +6,14 @@ even hard-codes ``prefetch(0)``, ref src/join/hash/join_compute_api.h:397).  Its
 single-GPU ``gdf_hash_partition`` (ref src/hashing.cu:559-654); this module is the layer one would put
 on top of it, built from the same C-ABI operators:
 
-    join      rows are block-distributed.  Every rank radix-partitions its local (key, global row id)
-              rows into G = world_size hash partitions with ``gdf_hash_partition`` (destination =
-              murmur3(key) & (G-1) / % G), exchanges the partition sizes and then the partitions
-              themselves with ONE ``all_to_all_single`` per column, joins what it received with the
-              single-GPU ``gdf_inner_join`` / ``gdf_left_join`` and maps the local result indices back
-              to global row ids.  Equal keys always meet on one rank; output stays sharded.
+    join      rows are block-distributed.  Every rank radix-partitions its local key column into
+              G = world_size destination ranges of {key, global row id} pairs (``gdfx_partition_pairs``:
+              the semantics of ``gdf_hash_partition`` - destination = fixed hash of the key - run by the
+              join's own histogram + write-combining scatter kernels), exchanges the range sizes and then
+              the ranges with ONE ``all_to_all_single`` per column, and joins what it received with
+              ``gdfx_join_pairs`` = the single-GPU ``gdf_inner_join`` / ``gdf_left_join`` kernels with the
+              travelling row ids as row tags, so the outputs are global row ids directly.  Equal keys
+              always meet on one rank; output stays sharded.
     group-by  two-phase: local ``gdf_group_by_sum`` first (at most #groups partial rows per rank,
               which also removes Zipf skew: a hot key becomes ONE partial row per rank), then the
               partials are hash-partitioned, exchanged and merged with a second ``gdf_group_by_sum``.
@@ -54,23 +56,34 @@ class GdfOps(object):
                                offsets, lib.GDF_HASH_MURMUR3)
         return [o.data for o in outs], list(offsets)
 
-    def _join(self, fn, lkeys, rkeys, lpayload, rpayload):
+    def partition_pairs(self, keys, id_base, nparts):
+        """Split a key column into nparts destination ranges of {key, global row id = id_base + position}.
+        Returns (keys_out, ids_out, start offsets).  One histogram + one write-combining scatter pass
+        (gdfx_partition_pairs: the join's own radix-partition kernels with a destination hash)."""
+        C, ffi, lib = self.C, self.ffi, self.lib
+        n = keys.numel()
+        out_k = torch.empty_like(keys)
+        out_i = torch.empty(n, dtype=torch.int32, device=keys.device)
+        offs = ffi.new("unsigned long long[]", nparts + 1)
+        lib.gdfx_partition_pairs(C.Column(keys).cdata, id_base, nparts, ffi.cast("void*", out_k.data_ptr()),
+                                 ffi.cast("int32_t*", out_i.data_ptr()), offs)
+        return out_k, out_i, [int(offs[p]) for p in range(nparts)]
+
+    def _join(self, kind, lkeys, rkeys, lids, rids):
+        """Join of exchanged {key, id} pairs; the outputs are the ids (the pairs' row tags ARE the ids
+        inside the partitioned join, so no separate index->id gather pass is needed)."""
         C, ffi, lib = self.C, self.ffi, self.lib
         L, R = C.Column(lkeys), C.Column(rkeys)
         out_l, out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
-        idx = ffi.new("int[]", [0])
-        fn(C.column_array([L]), 1, idx, C.column_array([R]), 1, idx, 1, 0, ffi.NULL, out_l, out_r, self.ctx)
-        # local result indices -> global row ids, in place on the library-owned buffers
-        if int(out_l.size):
-            lib.gdfx_remap_indices(out_l, ffi.cast("int32_t*", lpayload.data_ptr()), lpayload.numel())
-            lib.gdfx_remap_indices(out_r, ffi.cast("int32_t*", rpayload.data_ptr()), rpayload.numel())
+        lib.gdfx_join_pairs(kind, L.cdata, ffi.cast("int32_t*", lids.data_ptr()), R.cdata,
+                            ffi.cast("int32_t*", rids.data_ptr()), out_l, out_r)
         return C.library_owned_to_torch(out_l), C.library_owned_to_torch(out_r)
 
-    def inner_join(self, lkeys, rkeys, lpayload, rpayload):
-        return self._join(self.lib.gdf_inner_join, lkeys, rkeys, lpayload, rpayload)
+    def inner_join(self, lkeys, rkeys, lids, rids):
+        return self._join(0, lkeys, rkeys, lids, rids)
 
-    def left_join(self, lkeys, rkeys, lpayload, rpayload):
-        return self._join(self.lib.gdf_left_join, lkeys, rkeys, lpayload, rpayload)
+    def left_join(self, lkeys, rkeys, lids, rids):
+        return self._join(1, lkeys, rkeys, lids, rids)
 
     def group_by_sum(self, keys, vals):
         C, ffi, lib = self.C, self.ffi, self.lib
@@ -123,12 +136,6 @@ def shard_bounds(total_rows, world, rank):
 # ------------------------------------------------------------------------------------------------
 # distributed operators
 # ------------------------------------------------------------------------------------------------
-def _global_ids(n, offset, device):
-    if offset + n >= 2 ** 31:
-        raise ValueError("global row ids must fit int32 (gdf join indices are GDF_INT32)")
-    return torch.arange(offset, offset + n, dtype=torch.int32, device=device)
-
-
 def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops, group=None, timings=None):
     """Hash join of block-distributed key columns.
 
@@ -141,15 +148,10 @@ def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops
     world = dist.get_world_size(group)
     dev = left_keys.device
     ev = _Stamps(timings, dev)
-    lids = _global_ids(left_keys.numel(), left_offset, dev)
-    rids = _global_ids(right_keys.numel(), right_offset, dev)
-    if world == 1:
-        fn = ops.inner_join if kind == "inner" else ops.left_join
-        out = fn(left_keys, right_keys, lids, rids)
-        ev.mark("local_join")
-        return out
-    (lk, li), loff = ops.hash_partition([left_keys, lids], world)
-    (rk, ri), roff = ops.hash_partition([right_keys, rids], world)
+    if max(left_offset + left_keys.numel(), right_offset + right_keys.numel()) >= 2 ** 31:
+        raise ValueError("global row ids must fit int32 (gdf join indices are GDF_INT32)")
+    lk, li, loff = ops.partition_pairs(left_keys, left_offset, world)
+    rk, ri, roff = ops.partition_pairs(right_keys, right_offset, world)
     ev.mark("partition")
     (lk, li), _ = exchange([lk, li], loff, group)
     (rk, ri), _ = exchange([rk, ri], roff, group)

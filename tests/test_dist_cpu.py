@@ -30,6 +30,16 @@ class OracleOps(object):
         offsets = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int).tolist()
         return [torch.from_numpy(c.numpy()[order].copy()) for c in cols], offsets
 
+    def partition_pairs(self, keys, id_base, nparts):
+        import oracle
+        k = keys.numpy()
+        pid = oracle.partition_ids([k], nparts)
+        order = np.argsort(pid, kind="stable")
+        counts = np.bincount(pid, minlength=nparts)
+        offsets = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int).tolist()
+        ids = (np.arange(len(k), dtype=np.int64) + id_base).astype(np.int32)
+        return torch.from_numpy(k[order].copy()), torch.from_numpy(ids[order].copy()), offsets
+
     def _join(self, kind, lk, rk, lp, rp):
         import oracle
         li, ri = oracle.join(kind, [lk.numpy()], [rk.numpy()])

@@ -34,7 +34,7 @@ def _emulated_exchange(per_rank_cols, per_rank_offsets, world):
 @pytest.mark.parametrize("kind", ["inner", "left"])
 def test_sharded_join_matches_oracle(world, kind):
     ops = D.GdfOps()
-    P, B = 400_000, 50_000
+    P, B = 300_000, 50_000
     probe = np.random.randint(0, 2 * B, P).astype(np.int64)
     build = np.random.permutation(B).astype(np.int64)
     if kind == "left":
@@ -45,11 +45,11 @@ def test_sharded_join_matches_oracle(world, kind):
         blo, bhi = D.shard_bounds(len(build), world, r)
         lk = torch.from_numpy(probe[plo:phi]).cuda()
         rk = torch.from_numpy(build[blo:bhi]).cuda()
-        lid = torch.arange(plo, phi, dtype=torch.int32, device="cuda")
-        rid = torch.arange(blo, bhi, dtype=torch.int32, device="cuda")
-        cl, ol = ops.hash_partition([lk, lid], world)
-        cr, orr = ops.hash_partition([rk, rid], world)
-        shards_l.append(cl), offs_l.append(ol), shards_r.append(cr), offs_r.append(orr)
+        k1, i1, ol = ops.partition_pairs(lk, plo, world)
+        k2, i2, orr = ops.partition_pairs(rk, blo, world)
+        # every row keeps its key/id pairing and lands in exactly one destination range
+        assert sorted(zip(k1.cpu().tolist(), i1.cpu().tolist())) == sorted(zip(probe[plo:phi].tolist(), range(plo, phi)))
+        shards_l.append([k1, i1]), offs_l.append(ol), shards_r.append([k2, i2]), offs_r.append(orr)
     recv_l = _emulated_exchange(shards_l, offs_l, world)
     recv_r = _emulated_exchange(shards_r, offs_r, world)
     got_l, got_r = [], []
