@@ -12,7 +12,9 @@
 //     everything fully unrolled so that all per-row state stays in registers;
 //   * the op (sum / min / max), "count rows" and "keep a row count for AVG" are template parameters.
 // One CTA of 1024 threads per SM owns an 8192-slot cache (128 KB of shared memory); rows whose key is
-// not cached fold straight into the L2-resident global table with red.global.
+// not cached fold straight into the L2-resident global table with red.global.  The input stream is
+// staged one step ahead with cp.async (64 KB).  Variants that were measured and lost (miss queue, lock-step
+// inline-PTX cache phase, deferred misses with 768 threads): profiles/r01b_experiments.md.
 #pragma once
 
 constexpr int kFastThreads4 = 1024;
@@ -23,7 +25,15 @@ constexpr unsigned kGrabRows4 = 32 * 4 * 32;           // rows per warp per work
 struct FastCache4 {
   unsigned long long key[kCacheSlots4];   // way pairs are adjacent: one LDS.128 per set
   unsigned long long acc[kCacheSlots4];
+  // one-step-ahead staging of the input stream, 2 KB per warp: while a warp works on a step, the next
+  // step's 128 keys + 128 values are already on their way (cp.async)
+  uint4 stage[kFastThreads4 / 32][128];
 };
+static __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
 
 // Internal position hash.  h's top bits pick the cache set, its low bits the global slot.
 static __device__ __forceinline__ uint32_t mix_key(unsigned long long k) {
@@ -84,6 +94,19 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
   __syncthreads();
   const unsigned lane = lane_id();
   const bool vec_ok = VEC && aligned16(key_col) && aligned16(values);
+  uint4* const stage = cache.stage[threadIdx.x >> 5];
+  size_t staged_step = ~(size_t)0;  // row index of the step whose data is in (or on its way to) `stage`
+  // lane's 16-byte chunks of a full step: keys of rows 2*lane(+1), 64+2*lane(+1), then the same for values
+  auto prefetch_step = [&](size_t st) {
+    cp_async16(&stage[lane], reinterpret_cast<const unsigned long long*>(key_col) + st + 2 * lane);
+    cp_async16(&stage[32 + lane], reinterpret_cast<const unsigned long long*>(key_col) + st + 64 + 2 * lane);
+    if (!COUNT_ROWS) {
+      cp_async16(&stage[64 + lane], reinterpret_cast<const unsigned long long*>(values) + st + 2 * lane);
+      cp_async16(&stage[96 + lane], reinterpret_cast<const unsigned long long*>(values) + st + 64 + 2 * lane);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    staged_step = st;
+  };
 
   // one row: cache first, then the global table.  gk = key word of the row's first global slot,
   // loaded by the caller for all rows of a step before any of them is resolved.
@@ -122,14 +145,15 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
       int64_t v[4];
       bool live[4];
       if (vec_ok && step + 128 <= end) {  // lane reads rows step + 2*lane (+1) and step + 64 + 2*lane (+1)
+        if (staged_step != step) prefetch_step(step);  // first step of a grab: nothing was staged
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const size_t r = step + (size_t)q * 64 + 2 * lane;
-          const uint4 kr = ldg_stream(reinterpret_cast<const unsigned long long*>(key_col) + r);
+          const uint4 kr = stage[q * 32 + lane];
           k[2 * q] = ((unsigned long long)kr.y << 32) | kr.x;
           k[2 * q + 1] = ((unsigned long long)kr.w << 32) | kr.z;
           if (!COUNT_ROWS) {
-            const uint4 vr = ldg_stream(reinterpret_cast<const unsigned long long*>(values) + r);
+            const uint4 vr = stage[64 + q * 32 + lane];
             v[2 * q] = (int64_t)(((unsigned long long)vr.y << 32) | vr.x);
             v[2 * q + 1] = (int64_t)(((unsigned long long)vr.w << 32) | vr.z);
           } else {
@@ -137,6 +161,8 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
           }
           live[2 * q] = live[2 * q + 1] = true;
         }
+        // every lane reads back exactly the chunks it copied itself, so the buffer can be refilled at once
+        if (step + 256 <= end) prefetch_step(step + 128);
       } else {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
