@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every row count (debug only)")
     ap.add_argument("--only", default="", help="comma list of join,groupby,filter (debug only)")
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="N>1: rows cross NVLink inside the partition kernel (peer memory) or via NCCL all_to_all")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -437,6 +439,7 @@ def bench_dist(args, rank, world, local_rank):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api = Api("b200")
     ops = D.GdfOps()
+    peer = D.PeerExchange(ops) if args.exchange == "p2p" else None
     peak_gbs, peak_kind = load_peak()
     clocks = Clocks(local_rank)
     P, B = int(1e9 * args.scale), int(1e8 * args.scale)
@@ -457,7 +460,7 @@ def bench_dist(args, rank, world, local_rank):
         return int(t.item())
 
     # ---- parity properties at full size: every probe row appears exactly once, every pair joins equal keys
-    gl, gr = D.distributed_join("inner", probe, build, plo, blo, ops)
+    gl, gr = D.distributed_join("inner", probe, build, plo, blo, ops, peer=peer)
     pairs_local = gl.numel()
     pairs = all_sum(pairs_local)
     id_sum = all_sum(int(gl.long().sum().item()))
@@ -473,7 +476,7 @@ def bench_dist(args, rank, world, local_rank):
     timings = {}
 
     def step():
-        a, b = D.distributed_join("inner", probe, build, plo, blo, ops, timings=timings)
+        a, b = D.distributed_join("inner", probe, build, plo, blo, ops, timings=timings, peer=peer)
         del a, b
 
     def timed(fn, warmup, steps):
@@ -517,7 +520,7 @@ def bench_dist(args, rank, world, local_rank):
         def e2e_step():
             d_probe.copy_(h_probe, non_blocking=True)
             d_build.copy_(h_build, non_blocking=True)
-            a, b = D.distributed_join("inner", d_probe, d_build, plo, blo, ops)
+            a, b = D.distributed_join("inner", d_probe, d_build, plo, blo, ops, peer=peer)
             h_l[: a.numel()].copy_(a, non_blocking=True)
             h_r[: b.numel()].copy_(b, non_blocking=True)
             torch.cuda.synchronize()
@@ -535,7 +538,7 @@ def bench_dist(args, rank, world, local_rank):
                "data": "synthetic (seeded torch device RNG, SURVEY.md 8d)", "impl": "b200",
                "config": {"workload": JoinWorkload.name + ", rows block-distributed over %d ranks" % world,
                           "probe_rows": P, "build_rows": B, "key_dtype": "int64", "rows_counted": "probe+build",
-                          "parallelism": "hash-partition + NCCL all_to_all + local join (dp%d)" % world,
+                          "parallelism": ("partition kernel storing into NVLink peer memory + local join (dp%d)" if peer else "hash-partition + NCCL all_to_all + local join (dp%d)") % world,
                           "l2_policy": "per-rank inputs (%.1f GB) larger than L2, no flush" % (8 * (P + B) / world / 1e9)},
                "parity_properties_ok": parity_ok, "output_pairs": pairs, "phases_ms_rank0": phases,
                "kernels_rank0": kernels, "clocks": clocks.summarise(clocks.window(t0, t1)),
@@ -557,6 +560,8 @@ def bench_dist(args, rank, world, local_rank):
         if e2e:
             out["e2e"] = e2e
         print(json.dumps(out))
+    if peer:
+        peer.close()
     dist.destroy_process_group()
     return 0
 

@@ -28,3 +28,22 @@ gdf_error gdfx_partition_pairs(gdf_column *key, int32_t id_base, int num_partiti
  * gdf_column_free) hold those ids instead of positions, -1 = no partner. */
 gdf_error gdfx_join_pairs(int kind, gdf_column *left_key, const int32_t *left_ids, gdf_column *right_key,
                           const int32_t *right_ids, gdf_column *out_l, gdf_column *out_r);
+
+/* Fused partition + exchange over peer memory (multi-GPU layer, libgdf_b200/dist.py PeerExchange).
+ *   gdfx_partition_count         rows of `key` per destination (host array [num_partitions])
+ *   gdfx_partition_scatter_peer  one pass that writes every {key, id = id_base + position} pair straight
+ *                                into its destination's receive buffers: dst_keys[p] / dst_ids[p] are device
+ *                                pointers valid on THIS device - local buffers or peer buffers mapped with
+ *                                gdfx_peer_open, in which case the stores cross NVLink from inside the kernel -
+ *                                and dst_offsets[p] is this rank's first row inside destination p's buffers
+ *                                (host arrays, num_partitions <= 16)
+ *   gdfx_peer_alloc/open/close/free   cudaMalloc'd buffers shared between the ranks' processes through
+ *                                64-byte CUDA IPC handles */
+gdf_error gdfx_partition_count(gdf_column *key, int num_partitions, unsigned long long *counts);
+gdf_error gdfx_partition_scatter_peer(gdf_column *key, int32_t id_base, int num_partitions,
+                                      void * const *dst_keys, int32_t * const *dst_ids,
+                                      const unsigned long long *dst_offsets);
+gdf_error gdfx_peer_alloc(void **ptr, size_t bytes, char *handle64);
+gdf_error gdfx_peer_open(const char *handle64, void **ptr);
+gdf_error gdfx_peer_close(void *ptr);
+gdf_error gdfx_peer_free(void *ptr);

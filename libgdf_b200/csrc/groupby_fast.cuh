@@ -29,9 +29,12 @@ struct FastCache4 {
   // step's 128 keys + 128 values are already on their way (cp.async)
   uint4 stage[kFastThreads4 / 32][128];
 };
-static __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src)
+// The input stream is read once: L2 evict_first, so that it does not push the 64 MB global table out of L2
+// (ncu at full size before the hint: 21.0 GB of DRAM traffic for 16.0 GB of input).
+static __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "l"(policy)
                : "memory");
 }
 
@@ -97,12 +100,14 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
   uint4* const stage = cache.stage[threadIdx.x >> 5];
   size_t staged_step = ~(size_t)0;  // row index of the step whose data is in (or on its way to) `stage`
   // lane's 16-byte chunks of a full step: keys of rows 2*lane(+1), 64+2*lane(+1), then the same for values
+  uint64_t pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   auto prefetch_step = [&](size_t st) {
-    cp_async16(&stage[lane], reinterpret_cast<const unsigned long long*>(key_col) + st + 2 * lane);
-    cp_async16(&stage[32 + lane], reinterpret_cast<const unsigned long long*>(key_col) + st + 64 + 2 * lane);
+    cp_async16(&stage[lane], reinterpret_cast<const unsigned long long*>(key_col) + st + 2 * lane, pol_stream);
+    cp_async16(&stage[32 + lane], reinterpret_cast<const unsigned long long*>(key_col) + st + 64 + 2 * lane, pol_stream);
     if (!COUNT_ROWS) {
-      cp_async16(&stage[64 + lane], reinterpret_cast<const unsigned long long*>(values) + st + 2 * lane);
-      cp_async16(&stage[96 + lane], reinterpret_cast<const unsigned long long*>(values) + st + 64 + 2 * lane);
+      cp_async16(&stage[64 + lane], reinterpret_cast<const unsigned long long*>(values) + st + 2 * lane, pol_stream);
+      cp_async16(&stage[96 + lane], reinterpret_cast<const unsigned long long*>(values) + st + 64 + 2 * lane, pol_stream);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     staged_step = st;

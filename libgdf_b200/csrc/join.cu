@@ -27,6 +27,8 @@
 //     0xFFFFFFFF-hash sentinel collision cannot happen.
 //   * single 4/8-byte integer key columns take the radix-partitioned path of join_part.cuh so that
 //     every table probe is an L2 hit instead of a DRAM row miss.
+#include <cstring>
+
 #include "select.cuh"
 #include "table.cuh"
 
@@ -38,6 +40,9 @@ gdf_error partitioned_join(int kind, const gdf_column* probe_key, const gdf_colu
                            const int32_t* build_payload = nullptr);
 gdf_error partition_pairs(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* out_keys,
                           int32_t* out_ids, unsigned long long* h_offsets);
+gdf_error partition_count(const gdf_column* key, unsigned num_partitions, unsigned long long* h_counts);
+gdf_error partition_scatter_peer(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* const* dst_keys,
+                                 int32_t* const* dst_ids, const unsigned long long* dst_offsets);
 
 namespace {
 
@@ -630,4 +635,56 @@ extern "C" gdf_error gdfx_join_pairs(int kind, gdf_column* left_key, const int32
   e = gdfx_remap_indices(out_l, left_ids, L);
   if (e == GDF_SUCCESS) e = gdfx_remap_indices(out_r, right_ids, R);
   return e;
+}
+
+// ---- fused partition + exchange over peer memory ----
+extern "C" gdf_error gdfx_partition_count(gdf_column* key, int num_partitions, unsigned long long* counts) {
+  B200_REQUIRE(key != nullptr && counts != nullptr, GDF_DATASET_EMPTY);
+  B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
+  B200_REQUIRE(num_partitions >= 1, GDF_INVALID_API_CALL);
+  if (key->size == 0) {
+    for (int p = 0; p < num_partitions; ++p) counts[p] = 0;
+    return GDF_SUCCESS;
+  }
+  return partition_count(key, (unsigned)num_partitions, counts);
+}
+
+extern "C" gdf_error gdfx_partition_scatter_peer(gdf_column* key, int32_t id_base, int num_partitions,
+                                                 void* const* dst_keys, int32_t* const* dst_ids,
+                                                 const unsigned long long* dst_offsets) {
+  B200_REQUIRE(key && dst_keys && dst_ids && dst_offsets, GDF_DATASET_EMPTY);
+  B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
+  B200_REQUIRE(key->size < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
+  if (key->size == 0) return GDF_SUCCESS;
+  return partition_scatter_peer(key, id_base, (unsigned)num_partitions, dst_keys, dst_ids, dst_offsets);
+}
+
+// Receive buffers that other ranks (processes) can map: plain cudaMalloc + legacy CUDA IPC handle (64 bytes).
+extern "C" gdf_error gdfx_peer_alloc(void** ptr, size_t bytes, char* handle64) {
+  B200_REQUIRE(ptr != nullptr && handle64 != nullptr, GDF_DATASET_EMPTY);
+  B200_CUDA_TRY(cudaMalloc(ptr, bytes ? bytes : 1));
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, *ptr) != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return GDF_CUDA_ERROR;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  memcpy(handle64, &h, 64);
+  return GDF_SUCCESS;
+}
+extern "C" gdf_error gdfx_peer_open(const char* handle64, void** ptr) {
+  B200_REQUIRE(ptr != nullptr && handle64 != nullptr, GDF_DATASET_EMPTY);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  B200_CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GDF_SUCCESS;
+}
+extern "C" gdf_error gdfx_peer_close(void* ptr) {
+  B200_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return GDF_SUCCESS;
+}
+extern "C" gdf_error gdfx_peer_free(void* ptr) {
+  B200_CUDA_TRY(cudaFree(ptr));
+  return GDF_SUCCESS;
 }

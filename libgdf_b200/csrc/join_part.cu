@@ -166,11 +166,22 @@ struct ScatterSmem {
   unsigned long long gbase[kMaxParts];       // reserved global start of this tile's run
 };
 
+// Fused partition + exchange (multi-GPU layer): when `peer.on`, partition p's rows are written straight into
+// destination p's receive buffers - peer-GPU memory mapped through CUDA IPC, i.e. the stores travel over
+// NVLink from inside this kernel - instead of into one local array that an all-to-all would then move.
+constexpr int kMaxPeers = 16;
+struct PeerDst {
+  void* keys[kMaxPeers];
+  int32_t* ids[kMaxPeers];
+  int on;
+};
+
 template <typename KT, bool KEEP_NULLS, bool PREFETCH>
 __global__ void __launch_bounds__(kThreads, PREFETCH ? 2 : 3)
 part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
                     unsigned long long* __restrict__ cursors, KT* __restrict__ out_keys,
-                    int32_t* __restrict__ out_rows, const int32_t* __restrict__ payload, int32_t id_base) {
+                    int32_t* __restrict__ out_rows, const int32_t* __restrict__ payload, int32_t id_base,
+                    const PeerDst peer) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem<KT>& sm = *reinterpret_cast<ScatterSmem<KT>*>(smem_raw);
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -260,8 +271,10 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
       for (unsigned j = threadIdx.x; j < kept; j += kThreads) {
         const unsigned p = sm.pid[j];
         const unsigned long long gidx = sm.gbase[p] + (j - sm.lstart[p]);
-        out_keys[gidx] = sm.keys[j];
-        out_rows[gidx] = sm.rows[j];
+        KT* const ok = peer.on ? static_cast<KT*>(peer.keys[p]) : out_keys;
+        int32_t* const orow = peer.on ? peer.ids[p] : out_rows;
+        ok[gidx] = sm.keys[j];
+        orow[gidx] = sm.rows[j];
       }
     }
     // the next iteration's barrier (1) separates this copy-out from the next staging phase; the
@@ -901,10 +914,8 @@ unsigned pow2_at_least(size_t x) {
 }
 
 template <typename KT, bool KEEP_NULLS>
-gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, Scratch& rows_out,
-                         unsigned long long* d_totals /*device [nparts]*/, unsigned long long* d_cursors,
-                         unsigned long long* h_totals, size_t* kept, const int32_t* payload = nullptr,
-                         int32_t id_base = 0, KT* ext_keys = nullptr, int32_t* ext_rows = nullptr) {
+gdf_error partition_hist(const gdf_column* col, PartGeom g, unsigned long long* d_totals /*device [nparts]*/,
+                         unsigned long long* h_totals) {
   const KT* keys = static_cast<const KT*>(col->data);
   const size_t n = col->size;
   B200_CUDA_TRY(cudaMemsetAsync(d_totals, 0, g.nparts * sizeof(unsigned long long), 0));
@@ -915,20 +926,19 @@ gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, S
   }
   B200_CHECK_LAST();
   B200_CUDA_TRY(cudaMemcpy(h_totals, d_totals, g.nparts * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  unsigned long long h_cursors[kMaxParts], run = 0;
-  for (unsigned p = 0; p < g.nparts; ++p) {
-    h_cursors[p] = run;
-    run += h_totals[p];
-  }
-  *kept = (size_t)run;
+  return GDF_SUCCESS;
+}
+
+// h_cursors[p] = index of partition p's first row in its destination array (one shared array: the exclusive
+// scan of the counts; peer mode: this rank's offset inside destination p's receive buffer)
+template <typename KT, bool KEEP_NULLS>
+gdf_error partition_scatter(const gdf_column* col, PartGeom g, const unsigned long long* h_cursors,
+                            unsigned long long* d_cursors, KT* out_keys, int32_t* out_rows, const int32_t* payload,
+                            int32_t id_base, const PeerDst& peer) {
+  const KT* keys = static_cast<const KT*>(col->data);
+  const size_t n = col->size;
   B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  if (!ext_keys) {
-    B200_CUDA_TRY(keys_out.alloc((run ? run : 1) * sizeof(KT)));
-    B200_CUDA_TRY(rows_out.alloc((run ? run : 1) * sizeof(int32_t)));
-    ext_keys = keys_out.as<KT>();
-    ext_rows = rows_out.as<int32_t>();
-  }
-  static const bool prefetch = getenv("B200_SCATTER_PREFETCH") ? atoi(getenv("B200_SCATTER_PREFETCH")) != 0 : true;
+  static const bool prefetch = getenv("B200_SCATTER_PREFETCH") ? atoi(getenv("B200_SCATTER_PREFETCH")) != 0 : false;
   auto kern = prefetch ? part_scatter_kernel<KT, KEEP_NULLS, true> : part_scatter_kernel<KT, KEEP_NULLS, false>;
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<KT>)));
   int per_sm = 1;
@@ -938,11 +948,35 @@ gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, S
   const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
   {
     B200_TIMED("join_part_scatter");
-    kern<<<sblocks, kThreads, sizeof(ScatterSmem<KT>)>>>(keys, col->valid, n, g, d_cursors, ext_keys, ext_rows, payload,
-                                                        id_base);
+    kern<<<sblocks, kThreads, sizeof(ScatterSmem<KT>)>>>(keys, col->valid, n, g, d_cursors, out_keys, out_rows, payload,
+                                                        id_base, peer);
   }
   B200_CHECK_LAST();
   return GDF_SUCCESS;
+}
+
+template <typename KT, bool KEEP_NULLS>
+gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, Scratch& rows_out,
+                         unsigned long long* d_totals /*device [nparts]*/, unsigned long long* d_cursors,
+                         unsigned long long* h_totals, size_t* kept, const int32_t* payload = nullptr,
+                         int32_t id_base = 0, KT* ext_keys = nullptr, int32_t* ext_rows = nullptr) {
+  gdf_error e = partition_hist<KT, KEEP_NULLS>(col, g, d_totals, h_totals);
+  if (e != GDF_SUCCESS) return e;
+  unsigned long long h_cursors[kMaxParts], run = 0;
+  for (unsigned p = 0; p < g.nparts; ++p) {
+    h_cursors[p] = run;
+    run += h_totals[p];
+  }
+  *kept = (size_t)run;
+  if (!ext_keys) {
+    B200_CUDA_TRY(keys_out.alloc((run ? run : 1) * sizeof(KT)));
+    B200_CUDA_TRY(rows_out.alloc((run ? run : 1) * sizeof(int32_t)));
+    ext_keys = keys_out.as<KT>();
+    ext_rows = rows_out.as<int32_t>();
+  }
+  PeerDst none;
+  none.on = 0;
+  return partition_scatter<KT, KEEP_NULLS>(col, g, h_cursors, d_cursors, ext_keys, ext_rows, payload, id_base, none);
 }
 
 gdf_error read_u64(const unsigned long long* d, unsigned long long* h) {
@@ -1174,6 +1208,51 @@ gdf_error partition_pairs_typed(const gdf_column* key, int32_t id_base, unsigned
   }
   h_offsets[num_partitions] = run;
   return GDF_SUCCESS;
+}
+
+// Multi-GPU layer, fused path, step 1: rows per destination (host array [num_partitions]).
+gdf_error partition_count(const gdf_column* key, unsigned num_partitions, unsigned long long* h_counts) {
+  B200_REQUIRE(num_partitions >= 1 && num_partitions <= kMaxParts, GDF_INVALID_API_CALL);
+  PartGeom g;
+  g.nparts = num_partitions;
+  g.shift = 0;
+  g.dest = 1;
+  Scratch small;
+  B200_CUDA_TRY(small.alloc((size_t)num_partitions * sizeof(unsigned long long)));
+  switch (key->dtype) {
+    case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
+      return partition_hist<uint64_t, false>(key, g, small.as<unsigned long long>(), h_counts);
+    case GDF_INT32: case GDF_DATE32:
+      return partition_hist<uint32_t, false>(key, g, small.as<unsigned long long>(), h_counts);
+    default: return GDF_UNSUPPORTED_DTYPE;
+  }
+}
+
+// Step 2: scatter {key, id} pairs straight into the destinations' buffers (local or peer pointers).
+gdf_error partition_scatter_peer(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* const* dst_keys,
+                                 int32_t* const* dst_ids, const unsigned long long* dst_offsets) {
+  B200_REQUIRE(num_partitions >= 1 && num_partitions <= (unsigned)kMaxPeers, GDF_INVALID_API_CALL);
+  PartGeom g;
+  g.nparts = num_partitions;
+  g.shift = 0;
+  g.dest = 1;
+  PeerDst peer;
+  peer.on = 1;
+  for (int p = 0; p < kMaxPeers; ++p) {
+    peer.keys[p] = p < (int)num_partitions ? dst_keys[p] : nullptr;
+    peer.ids[p] = p < (int)num_partitions ? dst_ids[p] : nullptr;
+  }
+  Scratch small;
+  B200_CUDA_TRY(small.alloc((size_t)num_partitions * sizeof(unsigned long long)));
+  switch (key->dtype) {
+    case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
+      return partition_scatter<uint64_t, false>(key, g, dst_offsets, small.as<unsigned long long>(), nullptr, nullptr,
+                                                nullptr, id_base, peer);
+    case GDF_INT32: case GDF_DATE32:
+      return partition_scatter<uint32_t, false>(key, g, dst_offsets, small.as<unsigned long long>(), nullptr, nullptr,
+                                                nullptr, id_base, peer);
+    default: return GDF_UNSUPPORTED_DTYPE;
+  }
 }
 
 gdf_error partition_pairs(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* out_keys,

@@ -69,6 +69,44 @@ class GdfOps(object):
                                  ffi.cast("int32_t*", out_i.data_ptr()), offs)
         return out_k, out_i, [int(offs[p]) for p in range(nparts)]
 
+    def partition_count(self, keys, nparts):
+        ffi, lib = self.ffi, self.lib
+        counts = ffi.new("unsigned long long[]", nparts)
+        lib.gdfx_partition_count(self.C.Column(keys).cdata, nparts, counts)
+        return [int(counts[p]) for p in range(nparts)]
+
+    def partition_scatter_peer(self, keys, id_base, dst_key_ptrs, dst_id_ptrs, dst_offsets):
+        """One pass: every {key, id} pair is stored straight into its destination's buffers (device
+        addresses valid on this GPU: local memory or IPC-mapped peer memory)."""
+        ffi, lib = self.ffi, self.lib
+        n = len(dst_key_ptrs)
+        kp = ffi.new("void*[]", [ffi.cast("void*", p) for p in dst_key_ptrs])
+        ip = ffi.new("int32_t*[]", [ffi.cast("int32_t*", p) for p in dst_id_ptrs])
+        off = ffi.new("unsigned long long[]", [int(o) for o in dst_offsets])
+        lib.gdfx_partition_scatter_peer(self.C.Column(keys).cdata, id_base, n, kp, ip, off)
+
+    def peer_alloc(self, nbytes):
+        ffi, lib = self.ffi, self.lib
+        ptr = ffi.new("void**")
+        handle = ffi.new("char[64]")
+        lib.gdfx_peer_alloc(ptr, nbytes, handle)
+        return int(ffi.cast("uintptr_t", ptr[0])), bytes(ffi.buffer(handle, 64))
+
+    def peer_open(self, handle):
+        ffi, lib = self.ffi, self.lib
+        ptr = ffi.new("void**")
+        lib.gdfx_peer_open(ffi.new("char[64]", handle), ptr)
+        return int(ffi.cast("uintptr_t", ptr[0]))
+
+    def peer_close(self, address):
+        self.lib.gdfx_peer_close(self.ffi.cast("void*", address))
+
+    def peer_free(self, address):
+        self.lib.gdfx_peer_free(self.ffi.cast("void*", address))
+
+    def view(self, address, nelem, np_dtype):
+        return self.C._alias(address, nelem, np_dtype) if nelem else torch.empty(0, dtype=getattr(torch, np.dtype(np_dtype).name), device="cuda")
+
     def _join(self, kind, lkeys, rkeys, lids, rids):
         """Join of exchanged {key, id} pairs; the outputs are the ids (the pairs' row tags ARE the ids
         inside the partitioned join, so no separate index->id gather pass is needed)."""
@@ -126,6 +164,78 @@ def exchange(cols, offsets, group=None):
     return outs, recv_counts
 
 
+class PeerExchange(object):
+    """Fused partition + exchange: the partition kernel of every rank writes its {key, id} pairs straight
+    into the destination ranks' receive buffers through NVLink peer mappings (CUDA IPC), so the rows cross
+    the fabric from inside the scatter kernel and no separate all-to-all pass (read + send + write) exists.
+
+    Per exchange: one histogram pass, one all_gather of the world x world count matrix (which is also the
+    "everybody is done reading the previous contents" barrier, being stream-ordered after each rank's
+    previous work), one scatter pass, one 4-byte all_reduce ("all stores have landed").
+    Receive buffers are cudaMalloc'd once per name and grown only when a call needs more rows.
+    """
+
+    def __init__(self, ops, group=None):
+        self.ops, self.group = ops, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.slots = {}   # name -> {"cap", "itemsize", "mine": (kptr, iptr), "peers": ([kptr..], [iptr..])}
+        self._flag = None
+
+    def _ensure(self, name, rows, itemsize):
+        slot = self.slots.get(name)
+        if slot and slot["cap"] >= rows and slot["itemsize"] == itemsize:
+            return slot
+        if slot:
+            self._release(slot)
+        cap = max(1 << 20, (rows + (rows >> 3) + (1 << 20) - 1) >> 20 << 20)   # 12.5 % slack, 1 Mi-row granules
+        kptr, kh = self.ops.peer_alloc(cap * itemsize)
+        iptr, ih = self.ops.peer_alloc(cap * 4)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (kh, ih), group=self.group)
+        pk, pi = [], []
+        for r, (hk, hi) in enumerate(handles):
+            if r == self.rank:
+                pk.append(kptr), pi.append(iptr)
+            else:
+                pk.append(self.ops.peer_open(hk)), pi.append(self.ops.peer_open(hi))
+        slot = {"cap": cap, "itemsize": itemsize, "mine": (kptr, iptr), "peers": (pk, pi)}
+        self.slots[name] = slot
+        return slot
+
+    def _release(self, slot):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for r in range(self.world):
+            if r != self.rank:
+                self.ops.peer_close(slot["peers"][0][r]), self.ops.peer_close(slot["peers"][1][r])
+        dist.barrier(group=self.group)
+        self.ops.peer_free(slot["mine"][0]), self.ops.peer_free(slot["mine"][1])
+
+    def close(self):
+        for slot in self.slots.values():
+            self._release(slot)
+        self.slots = {}
+
+    def exchange_pairs(self, name, keys, id_base):
+        """Returns (keys, ids) this rank received: zero-copy views of its receive buffers, valid until the
+        next exchange under the same name."""
+        world, rank, dev = self.world, self.rank, keys.device
+        mine = torch.tensor(self.ops.partition_count(keys, world), dtype=torch.int64, device=dev)
+        allc = torch.empty(world * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        C = allc.view(world, world).cpu()                    # C[s][d] = rows rank s sends to rank d
+        recv_totals = C.sum(0)
+        slot = self._ensure(name, int(recv_totals.max().item()), keys.element_size())
+        offsets = [int(C[:rank, d].sum().item()) for d in range(world)]
+        self.ops.partition_scatter_peer(keys, id_base, slot["peers"][0], slot["peers"][1], offsets)
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(self._flag, group=self.group)        # stream-ordered: every rank's stores have landed
+        n = int(recv_totals[rank].item())
+        np_key = {8: np.int64, 4: np.int32}[keys.element_size()]
+        return self.ops.view(slot["mine"][0], n, np_key), self.ops.view(slot["mine"][1], n, np.int32)
+
+
 def shard_bounds(total_rows, world, rank):
     """Block distribution of total_rows over world ranks: [lo, hi) of `rank`."""
     per = (total_rows + world - 1) // world
@@ -136,7 +246,7 @@ def shard_bounds(total_rows, world, rank):
 # ------------------------------------------------------------------------------------------------
 # distributed operators
 # ------------------------------------------------------------------------------------------------
-def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops, group=None, timings=None):
+def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops, group=None, timings=None, peer=None):
     """Hash join of block-distributed key columns.
 
     left_keys / right_keys   this rank's shard of the (single, integer) key column
@@ -150,13 +260,20 @@ def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops
     ev = _Stamps(timings, dev)
     if max(left_offset + left_keys.numel(), right_offset + right_keys.numel()) >= 2 ** 31:
         raise ValueError("global row ids must fit int32 (gdf join indices are GDF_INT32)")
+    fn = ops.inner_join if kind == "inner" else ops.left_join
+    if peer is not None:   # fused partition + exchange over NVLink peer memory (PeerExchange)
+        lk, li = peer.exchange_pairs("left", left_keys, left_offset)
+        rk, ri = peer.exchange_pairs("right", right_keys, right_offset)
+        ev.mark("partition+exchange")
+        out = fn(lk, rk, li, ri)
+        ev.mark("local_join")
+        return out
     lk, li, loff = ops.partition_pairs(left_keys, left_offset, world)
     rk, ri, roff = ops.partition_pairs(right_keys, right_offset, world)
     ev.mark("partition")
     (lk, li), _ = exchange([lk, li], loff, group)
     (rk, ri), _ = exchange([rk, ri], roff, group)
     ev.mark("all_to_all")
-    fn = ops.inner_join if kind == "inner" else ops.left_join
     out = fn(lk, rk, li, ri)
     ev.mark("local_join")
     return out

@@ -96,3 +96,27 @@ def test_remap_indices_keeps_minus_one():
     libgdf.gdfx_remap_indices(col.cdata, ffi.cast("int32_t*", payload.data_ptr()), payload.numel())
     torch.cuda.synchronize()
     assert idx.cpu().tolist() == [100, -1, 103, 102, -1, 101]
+
+
+@pytest.mark.parametrize("world", [2, 5, 8])
+def test_partition_scatter_peer_matches_partition_pairs(world):
+    """The fused partition+exchange kernel with LOCAL destination buffers (the peer pointers of a real run
+    are ordinary device addresses to the kernel): every destination receives exactly the range that
+    gdfx_partition_pairs assigns to it, at the given offset."""
+    ops = D.GdfOps()
+    n, base = 700_003, 1000
+    keys = torch.from_numpy(np.random.randint(0, 1 << 40, n).astype(np.int64)).cuda()
+    pk, pi, offs = ops.partition_pairs(keys, base, world)
+    counts = ops.partition_count(keys, world)
+    bounds = offs + [n]
+    assert counts == [bounds[p + 1] - bounds[p] for p in range(world)]
+    pad = 17                                                     # this "rank" writes behind 17 foreign rows
+    dk = [torch.full((counts[p] + pad,), -7, dtype=torch.int64, device="cuda") for p in range(world)]
+    di = [torch.full((counts[p] + pad,), -7, dtype=torch.int32, device="cuda") for p in range(world)]
+    ops.partition_scatter_peer(keys, base, [t.data_ptr() for t in dk], [t.data_ptr() for t in di], [pad] * world)
+    torch.cuda.synchronize()
+    for p in range(world):
+        assert (dk[p][:pad] == -7).all() and (di[p][:pad] == -7).all()
+        got = sorted(zip(dk[p][pad:].cpu().tolist(), di[p][pad:].cpu().tolist()))
+        want = sorted(zip(pk[bounds[p]:bounds[p + 1]].cpu().tolist(), pi[bounds[p]:bounds[p + 1]].cpu().tolist()))
+        assert got == want

@@ -31,6 +31,13 @@ if has list; then
     echo "list $w rc=$?"
   done
 fi
+if has traffic; then
+  # DRAM bytes of the dominant kernels at FULL size (single-pass counters, no kernel replay)
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    -k regex:'part_probe|build_fast|select_stream' --csv --log-file $OUT/traffic_full.csv \
+    python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > $OUT/traffic_full.log 2>&1
+  echo "traffic rc=$?"
+fi
 if has full; then
   # quarter-size inputs: ncu's kernel replay saves/restores every written allocation; the partition
   # geometry (rows per partition, table bytes per partition) is the same as at full size.
