@@ -391,7 +391,16 @@ def kernel_bytes(name, wl):
     return None
 
 
-def roofline_for(res, wl, peak_gbs, peak_kind):
+def measured_traffic(kernel, scale):
+    """DRAM bytes per launch from the committed full-size ncu capture (profiles/r01c_traffic_full_size.json)."""
+    path = os.path.join(ROOT, "profiles", "r01c_traffic_full_size.json")
+    if scale != 1.0 or not os.path.isfile(path):
+        return None
+    rec = json.load(open(path)).get(kernel)
+    return (rec["dram_read"] + rec["dram_write"]) if rec else None
+
+
+def roofline_for(res, wl, peak_gbs, peak_kind, scale=1.0):
     ks = res["kernels"]
     if not ks:
         return None
@@ -402,7 +411,7 @@ def roofline_for(res, wl, peak_gbs, peak_kind):
         return {"kernel": top, "bound": "hbm", "achieved": None, "peak": peak_gbs, "unit": "GB/s", "frac": None, "traffic": None}
     achieved = nbytes / 1e9 / (per_launch_ms * 1e-3)
     return {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_kind,
+            "frac": achieved / peak_gbs, "traffic": measured_traffic(top, scale), "peak_source": peak_kind,
             "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": per_launch_ms,
             "share_of_step": ks[top]["ms_per_step"] / res["ms_per_step"]}
 
@@ -608,7 +617,7 @@ def main():
                     "config": {"workload": wl.name, "probe_rows": wl.P, "build_rows": wl.B, "key_dtype": "int64",
                                "rows_counted": "probe+build", "l2_policy": "inputs (8.8 GB) larger than L2, no flush",
                                "rmm": "pool"}})
-        roof = roofline_for(res, wl, peak_gbs, peak_kind)
+        roof = roofline_for(res, wl, peak_gbs, peak_kind, args.scale)
         if roof:
             out["roofline"] = roof
         out["gpu_launches"] = int(round(sum(k["launches_per_step"] for k in res["kernels"].values()) * args.steps)) if res["kernels"] else None
@@ -635,7 +644,7 @@ def main():
             res = run_workload(api, wl, args, peak_gbs, clocks)
             res["parity_properties_ok"] = ok
             res["groups"] = wl.groups
-            res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind)
+            res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale)
             workloads["groupby"] = res
             del wl
         except Exception as exc:
@@ -650,7 +659,7 @@ def main():
             res = run_workload(api, wl, args, peak_gbs, clocks)
             res["parity_properties_ok"] = ok
             res["selected"] = wl.selected
-            res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind)
+            res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale)
             workloads["filter"] = res
             del wl
         except Exception as exc:
