@@ -23,6 +23,7 @@
 //     costs one 32-byte L2 sector, and pre-aggregates equal keys inside a warp with match.any so a
 //     Zipf-hot key costs one atomic per warp instead of one per row;
 //   * extraction compacts only the small table, with one cursor atomic per warp.
+#include <cstdlib>
 #include <limits>
 #include <type_traits>
 
@@ -362,8 +363,9 @@ gdf_error groupby_fast(const KT* key_col, size_t n, const void* values, int op, 
   if (op == OP_MIN) identity = (int64_t)std::numeric_limits<VT>::max();
   if (op == OP_MAX) identity = (int64_t)std::numeric_limits<VT>::lowest();
   unsigned slots = pow2_at_least(2 * n);
-  const bool bounded = slots > kLevel1Slots;
-  if (bounded) slots = kLevel1Slots;
+  static const unsigned level1 = getenv("B200_GB_SLOTS_LOG2") ? 1u << atoi(getenv("B200_GB_SLOTS_LOG2")) : kLevel1Slots;  // lab knob
+  const bool bounded = slots > level1;
+  if (bounded) slots = level1;
   Scratch tab, cnt;
   B200_CUDA_TRY(tab.alloc(((size_t)slots + 1) * sizeof(FastSlot)));
   if (op == OP_AVG) B200_CUDA_TRY(cnt.alloc(((size_t)slots + 1) * sizeof(unsigned long long)));
@@ -377,11 +379,12 @@ gdf_error groupby_fast(const KT* key_col, size_t n, const void* values, int op, 
   const bool count_rows = op == OP_COUNT, with_cnt = op == OP_AVG;
   void (*kern)(const KT*, const VT*, size_t, FastSlot*, unsigned long long*, unsigned, unsigned, unsigned, int*,
                unsigned long long*) = nullptr;
-  if (count_rows) kern = build_fast_kernel_v4<KT, VT, OP_SUM, true, false>;
-  else if (with_cnt) kern = build_fast_kernel_v4<KT, VT, OP_SUM, false, true>;
-  else if (fold_op == OP_MIN) kern = build_fast_kernel_v4<KT, VT, OP_MIN, false, false>;
-  else if (fold_op == OP_MAX) kern = build_fast_kernel_v4<KT, VT, OP_MAX, false, false>;
-  else kern = build_fast_kernel_v4<KT, VT, OP_SUM, false, false>;
+  static const bool lean = getenv("B200_GROUPBY_LEAN") ? atoi(getenv("B200_GROUPBY_LEAN")) != 0 : false;  // lab knob
+  if (count_rows) kern = lean ? build_fast_kernel_v4<KT, VT, OP_SUM, true, false, true> : build_fast_kernel_v4<KT, VT, OP_SUM, true, false, false>;
+  else if (with_cnt) kern = lean ? build_fast_kernel_v4<KT, VT, OP_SUM, false, true, true> : build_fast_kernel_v4<KT, VT, OP_SUM, false, true, false>;
+  else if (fold_op == OP_MIN) kern = build_fast_kernel_v4<KT, VT, OP_MIN, false, false, false>;
+  else if (fold_op == OP_MAX) kern = build_fast_kernel_v4<KT, VT, OP_MAX, false, false, false>;
+  else kern = lean ? build_fast_kernel_v4<KT, VT, OP_SUM, false, false, true> : build_fast_kernel_v4<KT, VT, OP_SUM, false, false, false>;
   const int smem = (int)(sizeof(FastCache4) + (with_cnt ? kCacheSlots4 * sizeof(unsigned) : 0));
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   size_t want = (n + kGrabRows4 - 1) / kGrabRows4;                 // one warp-grab each
@@ -392,7 +395,11 @@ gdf_error groupby_fast(const KT* key_col, size_t n, const void* values, int op, 
     B200_TIMED("groupby_build_fast");
     kern<<<blocks, kFastThreads4, smem>>>(key_col, static_cast<const VT*>(values), n, tab.as<FastSlot>(),
                                           cnt.as<unsigned long long>(), slots - 1, slots,
-                                          bounded ? kProbeLimitL1 : slots, flags, cursor + 3);
+                                          (bounded ? kProbeLimitL1 : slots)
+#ifdef B200_LAB_GROUPBY
+                                              | (getenv("B200_LAB_GB") ? (unsigned)atoi(getenv("B200_LAB_GB")) << 28 : 0u)
+#endif
+                                          , flags, cursor + 3);
   }
   B200_CHECK_LAST();
   if (bounded) {

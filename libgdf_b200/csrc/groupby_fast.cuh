@@ -76,7 +76,7 @@ static __device__ __forceinline__ bool global_fold4(FastSlot* __restrict__ tab, 
   return false;
 }
 
-template <typename KT, typename IT, int FOLD, bool COUNT_ROWS, bool WITH_CNT>
+template <typename KT, typename IT, int FOLD, bool COUNT_ROWS, bool WITH_CNT, bool LEAN>
 __global__ void __launch_bounds__(kFastThreads4, 1)
 build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ values, size_t n,
                      FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt, unsigned mask, unsigned slots,
@@ -111,6 +111,48 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     staged_step = st;
+  };
+
+  // LEAN (additive folds): 32-bit shared addresses computed once (no generic->shared conversion per access)
+  // and the carry of the 64-bit shared-memory add examined at the END of the step, so the ATOMS round trip
+  // of a row is not waited for before the next row starts.
+  const uint32_t s_key = (uint32_t)__cvta_generic_to_shared(&cache.key[0]);
+  const uint32_t s_acc = (uint32_t)__cvta_generic_to_shared(&cache.acc[0]);
+  uint32_t lean_old[4], lean_slot[4];
+  bool lean_hit[4];
+  auto cache_try_lean = [&](int u, unsigned long long k, int64_t v, uint32_t h) -> bool {
+    const unsigned set2 = (h >> 20) * 2u;
+    ulonglong2 kk;
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(kk.x), "=l"(kk.y) : "r"(s_key + set2 * 8u));
+    lean_hit[u] = false;
+    int way = -1;
+    if (kk.x == k) way = 0;
+    else if (kk.y == k) way = 1;
+    if (way >= 0) {
+      lean_slot[u] = set2 + (unsigned)way;
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+                   : "=r"(lean_old[u])
+                   : "r"(s_acc + lean_slot[u] * 8u), "r"((uint32_t)(unsigned long long)v));
+      lean_hit[u] = true;
+      if (WITH_CNT) atomicAdd(&ccnt[lean_slot[u]], 1u);
+      return true;
+    }
+    if (kk.x == kEmptyKey || kk.y == kEmptyKey) {  // cold start only: claim a free way
+      if (kk.x == kEmptyKey) {
+        const unsigned long long prev = atomicCAS(&cache.key[set2], kEmptyKey, k);
+        if (prev == kEmptyKey || prev == k) way = 0;
+      }
+      if (way < 0) {
+        const unsigned long long prev = atomicCAS(&cache.key[set2 + 1], kEmptyKey, k);
+        if (prev == kEmptyKey || prev == k) way = 1;
+      }
+      if (way >= 0) {
+        cache_fold<FOLD>(&cache.acc[set2 + way], v);
+        if (WITH_CNT) atomicAdd(&ccnt[set2 + way], 1u);
+        return true;
+      }
+    }
+    return false;
   };
 
   // one row: cache first, then the global table.  gk = key word of the row's first global slot,
@@ -183,8 +225,12 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
       for (int u = 0; u < 4; ++u) {
         h[u] = mix_key(k[u]);
         miss[u] = live[u];
-        if (live[u] && k[u] != kEmptyKey) miss[u] = !cache_try(k[u], v[u], h[u]);
+        if (LEAN) lean_hit[u] = false;
+        if (live[u] && k[u] != kEmptyKey) miss[u] = LEAN ? !cache_try_lean(u, k[u], v[u], h[u]) : !cache_try(k[u], v[u], h[u]);
       }
+#ifdef B200_LAB_GROUPBY   // timing experiments of profiles/r01b_experiments.md (wrong results): -DB200_LAB_GROUPBY
+      if (probe_limit & 0x40000000u) continue;   // B200_LAB_GB=4: drop the global path entirely
+#endif
       // rows that missed the cache: first global slots fetched together, then resolved
       unsigned long long gk[4];
 #pragma unroll
@@ -196,8 +242,21 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
           fold(&tab[slots].acc, v[u], FOLD);
           if (WITH_CNT) atomicAdd(&cnt[slots], 1ull);
           flags[0] = 1;
-        } else if (!global_fold4<FOLD, WITH_CNT>(tab, cnt, mask, probe_limit, h[u] & mask, gk[u], k[u], v[u], 1ull)) {
+#ifdef B200_LAB_GROUPBY
+        } else if (probe_limit & 0x20000000u) {    // B200_LAB_GB=2: load the slot key, skip the fold
+          if (gk[u] == 12345ull) flags[1] = 1;
+#endif
+        } else if (!global_fold4<FOLD, WITH_CNT>(tab, cnt, mask, probe_limit & 0x0fffffffu, h[u] & mask, gk[u], k[u], v[u], 1ull)) {
           flags[1] = 1;
+        }
+      }
+      if (LEAN) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!lean_hit[u]) continue;
+          const uint32_t lo = (uint32_t)(unsigned long long)v[u];
+          const uint32_t up = (uint32_t)((unsigned long long)v[u] >> 32) + (uint32_t)((uint32_t)(lean_old[u] + lo) < lean_old[u]);
+          if (up) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(s_acc + lean_slot[u] * 8u + 4u), "r"(up) : "memory");
         }
       }
     }
