@@ -47,3 +47,10 @@ gdf_error gdfx_peer_alloc(void **ptr, size_t bytes, char *handle64);
 gdf_error gdfx_peer_open(const char *handle64, void **ptr);
 gdf_error gdfx_peer_close(void *ptr);
 gdf_error gdfx_peer_free(void *ptr);
+
+/* Multi-GPU layer, composite-key joins with NULLs (C5): row validity travels with the rows as a byte
+ * column.  gdfx_rows_valid_to_bytes: out[i] = 1 iff every column's validity bit i is set (no mask = all
+ * valid; the reference's row-valid rule, gdf_table.cuh:63-98).  gdfx_bytes_to_valid: LSB-first Arrow bitmask
+ * (ceil(rows/8) bytes) rebuilt from such a byte column on the receiving rank. */
+gdf_error gdfx_rows_valid_to_bytes(gdf_column **cols, int num_cols, int8_t *out);
+gdf_error gdfx_bytes_to_valid(const int8_t *in, size_t rows, gdf_valid_type *out);

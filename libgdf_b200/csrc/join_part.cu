@@ -83,7 +83,7 @@ struct PartGeom {
   unsigned dest;    // 1 = "destination rank" mode of the multi-GPU layer: pid = mulhi(remix(hash), nparts), a
                     // function that is independent of the top bits the receiver's local partitioning uses
   __device__ __forceinline__ unsigned pid(uint32_t h) const {
-    if (dest) return __umulhi(fmix32(h ^ 0x5bd1e995u), nparts);
+    if (dest & 1u) return __umulhi(fmix32(h ^ 0x5bd1e995u), nparts);
     return nparts == 1 ? 0u : (h >> shift);
   }
 };
@@ -435,6 +435,9 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
         mask[i] = t.mask[p];
         start[i] = slot_hash(h) & mask[i];
         lookup[i] = true;
+#ifdef B200_LAB_PROBE   // timing ablations (wrong results): g.dest bit 8 = no table look-up, bit 9 = no output stores
+        if (g.dest & 0x100u) { lookup[i] = false; cnt[i] = 1; first[i] = 0; }
+#endif
       }
       if (LEFT_LIKE) cnt[i] = 1;  // at least (row,-1)
     }
@@ -468,6 +471,9 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
   }
   if (threadIdx.x == 0) tile_out = tile_total ? atomicAdd(cursor, (unsigned long long)tile_total) : 0ull;
   if (!WRITE) return;
+#ifdef B200_LAB_PROBE
+  if (g.dest & 0x200u) return;
+#endif
   __syncthreads();
   size_t pos0 = (size_t)tile_out;
 #pragma unroll
@@ -680,6 +686,9 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
       first[i] = -1;
       cnt[i] = (LEFT_LIKE && have) ? 1u : 0u;
       lookup[i] = ok && key[i] != kEmptyKey;
+#ifdef B200_LAB_PROBE
+      if ((g.dest & 0x100u) && lookup[i]) { lookup[i] = false; cnt[i] = 1; first[i] = 0; }
+#endif
       const uint32_t h = KeyBits<KT>::hash(kraw);
       const unsigned p = g.pid(h);
       where[i] = (p << 24) | (slot_hash(h) & sm.part_mask[p]);
@@ -831,6 +840,9 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
       sm.tile_out[buf] = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
     }
     if (!WRITE) continue;  // count-only pass: the cursor is the result (tile_out is double-buffered)
+#ifdef B200_LAB_PROBE
+    if (g.dest & 0x200u) continue;
+#endif
     __syncthreads();
     size_t pos0 = (size_t)sm.tile_out[buf];
     for (unsigned w = 0; w < warp; ++w) pos0 += sm.warp_tot[buf][w];
@@ -1043,6 +1055,9 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   const bool left_like = kind != JOIN_INNER;
   PartGeom g;
   g.dest = 0;
+#ifdef B200_LAB_PROBE
+  if (getenv("B200_LAB_PROBE")) g.dest = (unsigned)atoi(getenv("B200_LAB_PROBE")) << 8;  // pid() tests dest & 1 only below
+#endif
   {
     unsigned np = pow2_at_least((B + kRowsPerPartition - 1) / kRowsPerPartition);
     if (np > kMaxParts) np = kMaxParts;

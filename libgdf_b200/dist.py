@@ -69,6 +69,49 @@ class GdfOps(object):
                                  ffi.cast("int32_t*", out_i.data_ptr()), offs)
         return out_k, out_i, [int(offs[p]) for p in range(nparts)]
 
+    def hash_partition_rows(self, cols, num_keys, nparts):
+        """gdf_hash_partition of all `cols`, hashing the first `num_keys` of them (MurmurHash3 row hash)."""
+        C, ffi, lib = self.C, self.ffi, self.lib
+        n = cols[0].numel()
+        if n == 0:
+            return [c.clone() for c in cols], [0] * nparts
+        ins = [C.Column(c) for c in cols]
+        outs = [C.Column(torch.empty_like(c)) for c in cols]
+        offsets = ffi.new("int[]", nparts)
+        lib.gdf_hash_partition(len(ins), C.column_array(ins), ffi.new("int[]", list(range(num_keys))), num_keys, nparts,
+                               C.column_array(outs), offsets, lib.GDF_HASH_MURMUR3)
+        return [o.data for o in outs], list(offsets)
+
+    def rows_valid_bytes(self, key_cols, valids):
+        """int8 column: 1 where every key column's validity bit is set (valids[i] = packed mask tensor or None)."""
+        C, ffi, lib = self.C, self.ffi, self.lib
+        n = key_cols[0].numel()
+        out = torch.empty(n, dtype=torch.int8, device=key_cols[0].device)
+        cols = [C.Column(k, v) for k, v in zip(key_cols, valids)]
+        lib.gdfx_rows_valid_to_bytes(C.column_array(cols), len(cols), ffi.cast("int8_t*", out.data_ptr()))
+        return out
+
+    def left_join_masked(self, lkeys, lok, rkeys, rok, lids, rids):
+        """gdf_left_join on N key columns whose row validity arrives as byte columns (lok / rok); outputs are
+        the travelling global row ids (-1 = no partner)."""
+        C, ffi, lib = self.C, self.ffi, self.lib
+
+        def with_mask(keys, ok):
+            n = keys[0].numel()
+            mask = torch.empty((n + 7) // 8, dtype=torch.uint8, device=keys[0].device)
+            lib.gdfx_bytes_to_valid(ffi.cast("int8_t*", ok.data_ptr()), n, ffi.cast("gdf_valid_type*", mask.data_ptr()))
+            return [C.Column(keys[0], mask)] + [C.Column(k) for k in keys[1:]]   # row-valid = AND over columns
+
+        L, R = with_mask(lkeys, lok), with_mask(rkeys, rok)
+        out_l, out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
+        idx = ffi.new("int[]", list(range(len(L))))
+        lib.gdf_left_join(C.column_array(L), len(L), idx, C.column_array(R), len(R), idx, len(L), 0, ffi.NULL, out_l, out_r,
+                          self.ctx)
+        if int(out_l.size):
+            lib.gdfx_remap_indices(out_l, ffi.cast("int32_t*", lids.data_ptr()), lids.numel())
+            lib.gdfx_remap_indices(out_r, ffi.cast("int32_t*", rids.data_ptr()), rids.numel())
+        return C.library_owned_to_torch(out_l), C.library_owned_to_torch(out_r)
+
     def partition_count(self, keys, nparts):
         ffi, lib = self.ffi, self.lib
         counts = ffi.new("unsigned long long[]", nparts)
@@ -275,6 +318,40 @@ def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops
     (rk, ri), _ = exchange([rk, ri], roff, group)
     ev.mark("all_to_all")
     out = fn(lk, rk, li, ri)
+    ev.mark("local_join")
+    return out
+
+
+def distributed_left_join_masked(left_keys, left_valids, right_keys, right_valids, left_offset, right_offset, ops,
+                                 group=None, timings=None):
+    """LEFT hash join on a COMPOSITE key with NULLs (BASELINE config C5: (int64,int32) key, 30 % null rows).
+
+    left_keys / right_keys     lists of this rank's key-column shards
+    left_valids / right_valids matching lists of packed validity masks (torch.uint8, LSB first) or None
+    Row validity (AND over the key columns) is turned into a byte column that travels with the rows:
+    {key columns, global row id, row-valid byte} are hash-partitioned on the key columns
+    (``gdf_hash_partition``), exchanged with one all_to_all per column, and joined per rank with
+    ``gdf_left_join`` on the rebuilt mask - so the reference's null rule holds unchanged across ranks:
+    a left row with a NULL key yields (l, -1), a right row with a NULL key never matches
+    (ref join_kernels.cuh:59,161,316).
+    """
+    world = dist.get_world_size(group)
+    dev = left_keys[0].device
+    ev = _Stamps(timings, dev)
+    nk = len(left_keys)
+    lids = torch.arange(left_offset, left_offset + left_keys[0].numel(), dtype=torch.int32, device=dev)
+    rids = torch.arange(right_offset, right_offset + right_keys[0].numel(), dtype=torch.int32, device=dev)
+    lok = ops.rows_valid_bytes(left_keys, left_valids)
+    rok = ops.rows_valid_bytes(right_keys, right_valids)
+    lcols, rcols = list(left_keys) + [lids, lok], list(right_keys) + [rids, rok]
+    if world > 1:
+        lcols, loff = ops.hash_partition_rows(lcols, nk, world)
+        rcols, roff = ops.hash_partition_rows(rcols, nk, world)
+        ev.mark("partition")
+        lcols, _ = exchange(lcols, loff, group)
+        rcols, _ = exchange(rcols, roff, group)
+        ev.mark("all_to_all")
+    out = ops.left_join_masked(lcols[:nk], lcols[nk + 1], rcols[:nk], rcols[nk + 1], lcols[nk], rcols[nk])
     ev.mark("local_join")
     return out
 

@@ -40,6 +40,33 @@ class OracleOps(object):
         ids = (np.arange(len(k), dtype=np.int64) + id_base).astype(np.int32)
         return torch.from_numpy(k[order].copy()), torch.from_numpy(ids[order].copy()), offsets
 
+    def hash_partition_rows(self, cols, num_keys, nparts):
+        import oracle
+        pid = oracle.partition_ids([c.numpy() for c in cols[:num_keys]], nparts)
+        order = np.argsort(pid, kind="stable")
+        counts = np.bincount(pid, minlength=nparts)
+        offsets = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int).tolist()
+        return [torch.from_numpy(c.numpy()[order].copy()) for c in cols], offsets
+
+    def rows_valid_bytes(self, key_cols, valids):
+        from oracle import np_oracle
+        n = key_cols[0].numel()
+        ok = np.ones(n, dtype=bool)
+        for v in valids:
+            ok &= np_oracle.unpack_valid(None if v is None else v.numpy(), n)
+        return torch.from_numpy(ok.astype(np.int8))
+
+    def left_join_masked(self, lkeys, lok, rkeys, rok, lids, rids):
+        import oracle
+        from oracle import np_oracle
+        lv = [np_oracle.pack_valid(lok.numpy() != 0)] + [None] * (len(lkeys) - 1)
+        rv = [np_oracle.pack_valid(rok.numpy() != 0)] + [None] * (len(rkeys) - 1)
+        li, ri = oracle.join(oracle.JOIN_LEFT, [k.numpy() for k in lkeys], [k.numpy() for k in rkeys], lv, rv)
+        lpn, rpn = lids.numpy(), rids.numpy()
+        gl = np.where(li >= 0, lpn[np.maximum(li, 0)], -1).astype(np.int32) if len(li) else li
+        gr = np.where(ri >= 0, rpn[np.maximum(ri, 0)], -1).astype(np.int32) if len(ri) else ri
+        return torch.from_numpy(gl), torch.from_numpy(gr)
+
     def _join(self, kind, lk, rk, lp, rp):
         import oracle
         li, ri = oracle.join(kind, [lk.numpy()], [rk.numpy()])
@@ -62,6 +89,18 @@ class OracleOps(object):
             return keys.clone(), vals.clone()
         k, a = oracle.groupby(oracle.OP_SUM, [keys.numpy()], vals.numpy())
         return torch.from_numpy(k[0]), torch.from_numpy(a)
+
+
+def _c5_tables(rng):
+    """BASELINE config C5 at test size: (int64,int32) key, 30 % null rows (one of the two masks cleared)."""
+    nl, nr = 30_000, 3_000
+    l = [rng.randint(0, nr, nl).astype(np.int64), rng.randint(0, 4, nl).astype(np.int32)]
+    r = [rng.randint(0, nr, nr).astype(np.int64), rng.randint(0, 4, nr).astype(np.int32)]
+
+    def masks(n):
+        null_rows, which = rng.rand(n) < 0.3, rng.rand(n) < 0.5
+        return [np.packbits(~(null_rows & which), bitorder="little"), np.packbits(~(null_rows & ~which), bitorder="little")]
+    return l, r, masks(nl), masks(nr)
 
 
 def _free_port():
@@ -88,6 +127,19 @@ def _worker(rank, world, port, case, tmpdir):
             plo, phi = D.shard_bounds(len(probe), world, rank)
             blo, bhi = D.shard_bounds(len(build), world, rank)
             gl, gr = D.distributed_join(case, torch.from_numpy(probe[plo:phi]), torch.from_numpy(build[blo:bhi]), plo, blo, ops)
+            np.save(os.path.join(tmpdir, "l%d.npy" % rank), gl.numpy())
+            np.save(os.path.join(tmpdir, "r%d.npy" % rank), gr.numpy())
+        elif case == "c5":
+            l, r, lv, rv = _c5_tables(rng)
+            plo, phi = D.shard_bounds(len(l[0]), world, rank)
+            blo, bhi = D.shard_bounds(len(r[0]), world, rank)
+
+            def shard_mask(mask, lo, hi):   # re-pack the shard's bits (shards do not start on byte boundaries)
+                from oracle import np_oracle
+                return torch.from_numpy(np_oracle.pack_valid(np_oracle.unpack_valid(mask, len(mask) * 8)[lo:hi]))
+            gl, gr = D.distributed_left_join_masked(
+                [torch.from_numpy(c[plo:phi].copy()) for c in l], [shard_mask(m, plo, phi) for m in lv],
+                [torch.from_numpy(c[blo:bhi].copy()) for c in r], [shard_mask(m, blo, bhi) for m in rv], plo, blo, ops)
             np.save(os.path.join(tmpdir, "l%d.npy" % rank), gl.numpy())
             np.save(os.path.join(tmpdir, "r%d.npy" % rank), gr.numpy())
         elif case == "groupby":
@@ -158,3 +210,16 @@ def test_distributed_groupby_matches_single_table_oracle(world, tmp_path):
     gv = np.concatenate([np.load(tmp_path / ("v%d.npy" % r)) for r in range(world)])
     assert len(np.unique(gk)) == len(gk), "a key landed on two ranks"
     assert sorted(zip(gk.tolist(), gv.tolist())) == sorted(zip(ok[0].tolist(), oa.tolist()))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_c5_left_join_composite_key_with_nulls(world, tmp_path):
+    import oracle
+    _run(world, "c5", tmp_path)
+    l, r, lv, rv = _c5_tables(np.random.RandomState(1234))
+    ol, orr = oracle.join(oracle.JOIN_LEFT, l, r, lv, rv)
+    gl = np.concatenate([np.load(tmp_path / ("l%d.npy" % k)) for k in range(world)])
+    gr = np.concatenate([np.load(tmp_path / ("r%d.npy" % k)) for k in range(world)])
+    got, want = np.stack([gl, gr], 1), np.stack([ol, orr], 1)
+    np.testing.assert_array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
+    assert len(gl) >= len(l[0]) and (gr == -1).sum() > 0.25 * len(l[0])      # null / unmatched left rows are kept

@@ -120,3 +120,45 @@ def test_partition_scatter_peer_matches_partition_pairs(world):
         got = sorted(zip(dk[p][pad:].cpu().tolist(), di[p][pad:].cpu().tolist()))
         want = sorted(zip(pk[bounds[p]:bounds[p + 1]].cpu().tolist(), pi[bounds[p]:bounds[p + 1]].cpu().tolist()))
         assert got == want
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_c5_left_join_composite_key_with_nulls(world):
+    """BASELINE config C5 at test size through the multi-GPU operators (row validity travels as a byte
+    column, gdf_hash_partition on both key columns, gdf_left_join on the rebuilt mask), exchange emulated."""
+    from oracle import np_oracle
+    ops = D.GdfOps()
+    nl, nr = 200_000, 20_000
+    l = [np.random.randint(0, nr, nl).astype(np.int64), np.random.randint(0, 4, nl).astype(np.int32)]
+    r = [np.random.randint(0, nr, nr).astype(np.int64), np.random.randint(0, 4, nr).astype(np.int32)]
+
+    def masks(n):
+        null_rows, which = np.random.rand(n) < 0.3, np.random.rand(n) < 0.5
+        return [np.packbits(~(null_rows & which), bitorder="little"), np.packbits(~(null_rows & ~which), bitorder="little")]
+    lv, rv = masks(nl), masks(nr)
+
+    def shard(cols, valids, lo, hi):
+        keys = [torch.from_numpy(c[lo:hi].copy()).cuda() for c in cols]
+        vs = [torch.from_numpy(np_oracle.pack_valid(np_oracle.unpack_valid(m, len(m) * 8)[lo:hi])).cuda() for m in valids]
+        ok = ops.rows_valid_bytes(keys, vs)
+        want_ok = np.ones(hi - lo, dtype=bool)
+        for m in valids:
+            want_ok &= np_oracle.unpack_valid(m, len(m) * 8)[lo:hi]
+        np.testing.assert_array_equal(ok.cpu().numpy().astype(bool), want_ok)
+        ids = torch.arange(lo, hi, dtype=torch.int32, device="cuda")
+        return ops.hash_partition_rows(keys + [ids, ok], 2, world)
+
+    lparts, rparts = [], []
+    for k in range(world):
+        lparts.append(shard(l, lv, *D.shard_bounds(nl, world, k)))
+        rparts.append(shard(r, rv, *D.shard_bounds(nr, world, k)))
+    recv_l = _emulated_exchange([p[0] for p in lparts], [p[1] for p in lparts], world)
+    recv_r = _emulated_exchange([p[0] for p in rparts], [p[1] for p in rparts], world)
+    gl, gr = [], []
+    for k in range(world):
+        a, b = ops.left_join_masked(recv_l[k][:2], recv_l[k][3], recv_r[k][:2], recv_r[k][3], recv_l[k][2], recv_r[k][2])
+        gl.append(a.cpu().numpy()), gr.append(b.cpu().numpy())
+    gl, gr = np.concatenate(gl), np.concatenate(gr)
+    ol, orr = oracle.join(oracle.JOIN_LEFT, l, r, lv, rv)
+    got, want = np.stack([gl, gr], 1), np.stack([ol, orr], 1)
+    np.testing.assert_array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
