@@ -37,7 +37,8 @@ namespace b200 {
 // radix-partitioned single-key path (join_part.cu)
 gdf_error partitioned_join(int kind, const gdf_column* probe_key, const gdf_column* build_key, bool flip,
                            gdf_column* out_l, gdf_column* out_r, bool* handled, const int32_t* probe_payload = nullptr,
-                           const int32_t* build_payload = nullptr);
+                           const int32_t* build_payload = nullptr, const gdf_column* probe_key2 = nullptr,
+                           const gdf_column* build_key2 = nullptr);
 gdf_error partition_pairs(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* out_keys,
                           int32_t* out_ids, unsigned long long* h_offsets);
 gdf_error partition_count(const gdf_column* key, unsigned num_partitions, unsigned long long* h_counts);
@@ -402,6 +403,9 @@ gdf_error join_call(int kind, int num_cols, gdf_column** leftcol, gdf_column** r
   gdf_error e = GDF_SUCCESS;
   bool handled = false;
   if (num_cols == 1) e = partitioned_join(kind, probe_cols[0], build_cols[0], flip, out_l, out_r, &handled);
+  else if (num_cols == 2)  // (4/8-byte integer, 4-byte integer) composite keys, e.g. C5's (int64,int32)
+    e = partitioned_join(kind, probe_cols[0], build_cols[0], flip, out_l, out_r, &handled, nullptr, nullptr, probe_cols[1],
+                         build_cols[1]);
   if (e == GDF_SUCCESS && !handled) {
     TableView probe, build;
     make_view(probe, probe_cols, num_cols);

@@ -74,6 +74,13 @@ template <> struct KeyBits<uint32_t> {
 
 // Slot index inside a partition's table: all rows of one partition share the top bits of h, so the
 // slot comes from a multiplicative re-mix whose middle bits depend on every bit of h.
+// Composite (key, 4-byte second key) rows: the second key is folded into the position hash and stored in the
+// slot's spare word, so (int64,int32) / (int32,int32) keys take the same partitioned path as single keys.
+static __device__ __forceinline__ uint32_t with_k2(uint32_t h, uint32_t k2) {
+  h = (h ^ (k2 * 0x9E3779B1u)) * 0x85EBCA77u;
+  return h ^ (h >> 15);
+}
+
 // Home slots are EVEN: a probe reads the aligned 32-byte pair {home, home+1} in one sector.
 static __device__ __forceinline__ uint32_t slot_hash(uint32_t h) { return ((h * 0x9E3779B1u) >> 7) & ~1u; }
 
@@ -94,12 +101,13 @@ struct PartGeom {
 template <typename KT, bool KEEP_NULLS>
 __global__ void __launch_bounds__(kThreads)
 part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
-                 unsigned long long* __restrict__ totals) {
+                 unsigned long long* __restrict__ totals, const uint32_t* __restrict__ k2,
+                 const gdf_valid_type* __restrict__ valid2) {
   __shared__ unsigned hist[kMaxParts];
   for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) hist[p] = 0;
   __syncthreads();
   const size_t stride = (size_t)gridDim.x * kThreads;
-  if (valid == nullptr && aligned16(keys)) {  // no mask: 128-bit loads, 4 in flight per thread
+  if (valid == nullptr && valid2 == nullptr && k2 == nullptr && aligned16(keys)) {  // no mask: 128-bit loads, 4 in flight per thread
     constexpr int VEC = 16 / (int)sizeof(KT), U = 4;
     const size_t nvec = n / VEC;
     const uint4* k4 = reinterpret_cast<const uint4*>(keys);
@@ -135,8 +143,13 @@ part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__
       for (int u = 0; u < U; ++u) {
         const size_t r = r0 + (size_t)u * stride;
         if (r >= n) continue;
-        if (bit_valid(valid, r)) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(k[u]))], 1u);
-        else if (KEEP_NULLS) atomicAdd(&hist[(unsigned)r & (g.nparts - 1)], 1u);
+        if (bit_valid(valid, r) && bit_valid(valid2, r)) {
+          uint32_t h = KeyBits<KT>::hash(k[u]);
+          if (k2) h = with_k2(h, k2[r]);
+          atomicAdd(&hist[g.pid(h)], 1u);
+        } else if (KEEP_NULLS) {
+          atomicAdd(&hist[(unsigned)r & (g.nparts - 1)], 1u);
+        }
       }
     }
   }
@@ -176,14 +189,21 @@ struct PeerDst {
   int on;
 };
 
-template <typename KT, bool KEEP_NULLS, bool PREFETCH>
-__global__ void __launch_bounds__(kThreads, PREFETCH ? 2 : 3)
+struct ScatterK2 {  // second key column of composite keys (HAS_K2)
+  const uint32_t* in;
+  const gdf_valid_type* valid2;
+  uint32_t* out;
+};
+
+template <typename KT, bool KEEP_NULLS, bool PREFETCH, bool HAS_K2>
+__global__ void __launch_bounds__(kThreads, (PREFETCH || HAS_K2) ? 2 : 3)
 part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
                     unsigned long long* __restrict__ cursors, KT* __restrict__ out_keys,
                     int32_t* __restrict__ out_rows, const int32_t* __restrict__ payload, int32_t id_base,
-                    const PeerDst peer) {
+                    const PeerDst peer, const ScatterK2 k2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem<KT>& sm = *reinterpret_cast<ScatterSmem<KT>*>(smem_raw);
+  uint32_t* const sk2 = reinterpret_cast<uint32_t*>(smem_raw + sizeof(ScatterSmem<KT>));  // [kScatterTile], HAS_K2 only
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   const size_t tiles = (n + kScatterTile - 1) / kScatterTile;
   for (unsigned p = threadIdx.x; p < 2 * kMaxParts; p += kThreads) (&sm.hist[0][0])[p] = 0;
@@ -208,13 +228,19 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
     for (int i = 0; i < kScatterRows; ++i) k[i] = knext[i];
     if (PREFETCH) load_tile(tile + gridDim.x);  // in flight during all the shared-memory phases below
     unsigned rp[kScatterRows];    // rank << 16 | pid, 0xffff = dropped, bit 15 = NULL-key row
+    uint32_t k2v[HAS_K2 ? kScatterRows : 1];
 #pragma unroll
     for (int i = 0; i < kScatterRows; ++i) {
       const size_t r = wbase + (size_t)i * 32 + lane;
       bool keep = r < n;
       unsigned p = 0, nullbit = 0;
+      if (HAS_K2) k2v[i] = keep ? k2.in[r] : 0u;
       if (keep) {
-        if (bit_valid(valid, r)) p = g.pid(KeyBits<KT>::hash(k[i]));
+        if (bit_valid(valid, r) && (!HAS_K2 || bit_valid(k2.valid2, r))) {
+          uint32_t h = KeyBits<KT>::hash(k[i]);
+          if (HAS_K2) h = with_k2(h, k2v[i]);
+          p = g.pid(h);
+        }
         else if (KEEP_NULLS) { p = (unsigned)r & (g.nparts - 1); nullbit = 0x8000u; }
         else keep = false;
       }
@@ -263,6 +289,7 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
       sm.keys[at] = k[i];
       sm.rows[at] = (rp[i] & 0x8000u) ? ~r : r;
       sm.pid[at] = (unsigned short)p;
+      if (HAS_K2) sk2[at] = k2v[i];
     }
     __syncthreads();  // (3) staged tile + gbase complete
     {  // element-parallel copy-out: consecutive threads take consecutive staged elements, which are
@@ -275,6 +302,7 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
         int32_t* const orow = peer.on ? peer.ids[p] : out_rows;
         ok[gidx] = sm.keys[j];
         orow[gidx] = sm.rows[j];
+        if (HAS_K2) k2.out[gidx] = sk2[j];
       }
     }
     // the next iteration's barrier (1) separates this copy-out from the next staging phase; the
@@ -290,6 +318,8 @@ struct Pairs {
   const int32_t* rows;
   const gdf_valid_type* valid;
   size_t n;
+  const uint32_t* k2;             // second key of a composite key (nullptr: single key)
+  const gdf_valid_type* valid2;   // its mask (unpartitioned pairs only)
 };
 
 struct Tables {
@@ -311,6 +341,7 @@ part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[
   const size_t tile_lo = (size_t)blockIdx.x * kBuildTile;
   unsigned long long key[U], prev[U];
   int32_t row[U];
+  uint32_t pad[U];
   Slot* tab[U];
   unsigned s[U], mask[U];
   bool live[U];
@@ -320,16 +351,19 @@ part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[
     live[u] = i < b.n;
     key[u] = 0;
     row[u] = 0;
+    pad[u] = 0;
     if (live[u]) {
       row[u] = b.rows ? b.rows[i] : (int32_t)i;
-      if (!b.rows && !bit_valid(b.valid, i)) live[u] = false;
+      if (!b.rows && !(bit_valid(b.valid, i) && bit_valid(b.valid2, i))) live[u] = false;
       key[u] = (unsigned long long)b.keys[i];
+      if (b.k2) pad[u] = b.k2[i];
     }
     if (live[u] && key[u] == kEmptyKey) {
       flags[1] = 1;
       live[u] = false;
     }
-    const uint32_t h = KeyBits<KT>::hash((KT)key[u]);
+    uint32_t h = KeyBits<KT>::hash((KT)key[u]);
+    if (b.k2) h = with_k2(h, pad[u]);
     const unsigned p = g.pid(h);
     tab[u] = t.slots + t.offset[p];
     mask[u] = t.mask[p];
@@ -351,6 +385,7 @@ part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[
       if (!((pend >> u) & 1u)) continue;
       if (prev[u] == kEmptyKey) {  // claimed
         tab[u][s[u]].row = row[u];
+        tab[u][s[u]].pad = (int32_t)pad[u];
         pend &= ~(1u << u);
       } else {
         if (prev[u] == key[u]) flags[0] = 1;  // duplicate build key
@@ -387,7 +422,7 @@ static __device__ __forceinline__ Slot ld_slot(const Slot* p) {
   Slot s;
   s.key = ((unsigned long long)raw.y << 32) | raw.x;
   s.row = (int32_t)raw.z;
-  s.pad = 0;
+  s.pad = (int32_t)raw.w;
   return s;
 }
 
@@ -403,11 +438,13 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
   unsigned long long key[kProbeRows];
   int32_t prow[kProbeRows], first[kProbeRows];
   unsigned cnt[kProbeRows], start[kProbeRows], mask[kProbeRows];
+  int32_t k2v[kProbeRows];
   const Slot* tab[kProbeRows];
   bool lookup[kProbeRows];
 #pragma unroll
   for (int i = 0; i < kProbeRows; ++i) {
     const size_t j = tile_base + (size_t)i * kThreads + threadIdx.x;
+    k2v[i] = 0;
     cnt[i] = 0;
     first[i] = -1;
     lookup[i] = false;
@@ -426,10 +463,12 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
         prow[i] = ok ? tag : ~tag;
       } else {
         prow[i] = (int32_t)j;
-        ok = bit_valid(pr.valid, j);
+        ok = bit_valid(pr.valid, j) && bit_valid(pr.valid2, j);
       }
+      if (pr.k2) k2v[i] = (int32_t)pr.k2[j];
       if (ok && key[i] != kEmptyKey) {
-        const uint32_t h = KeyBits<KT>::hash(kraw);
+        uint32_t h = KeyBits<KT>::hash(kraw);
+        if (pr.k2) h = with_k2(h, (uint32_t)k2v[i]);
         const unsigned p = g.pid(h);
         tab[i] = t.slots + t.offset[p];
         mask[i] = t.mask[p];
@@ -453,7 +492,7 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
     unsigned s = start[i], c = 0;
     Slot cur = s0[i];
     while (cur.key != kEmptyKey) {
-      if (cur.key == key[i]) {
+      if (cur.key == key[i] && cur.pad == k2v[i]) {  // pad is 0 on both sides for single keys
         if (c == 0) first[i] = cur.row;
         ++c;
         if (UNIQUE) break;
@@ -486,7 +525,7 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
       unsigned s = start[i];
       Slot cur = ld_slot(tab[i] + s);
       while (cur.key != kEmptyKey) {
-        if (cur.key == key[i]) {
+        if (cur.key == key[i] && cur.pad == k2v[i]) {
           out_probe[pos] = prow[i];
           out_build[pos] = cur.row;
           ++pos;
@@ -927,14 +966,16 @@ unsigned pow2_at_least(size_t x) {
 
 template <typename KT, bool KEEP_NULLS>
 gdf_error partition_hist(const gdf_column* col, PartGeom g, unsigned long long* d_totals /*device [nparts]*/,
-                         unsigned long long* h_totals) {
+                         unsigned long long* h_totals, const gdf_column* col2 = nullptr) {
   const KT* keys = static_cast<const KT*>(col->data);
   const size_t n = col->size;
   B200_CUDA_TRY(cudaMemsetAsync(d_totals, 0, g.nparts * sizeof(unsigned long long), 0));
   const int blocks = sm_count() * 4;
   {
     B200_TIMED("join_part_hist");
-    part_hist_kernel<KT, KEEP_NULLS><<<blocks, kThreads>>>(keys, col->valid, n, g, d_totals);
+    part_hist_kernel<KT, KEEP_NULLS><<<blocks, kThreads>>>(keys, col->valid, n, g, d_totals,
+                                                           col2 ? static_cast<const uint32_t*>(col2->data) : nullptr,
+                                                           col2 ? col2->valid : nullptr);
   }
   B200_CHECK_LAST();
   B200_CUDA_TRY(cudaMemcpy(h_totals, d_totals, g.nparts * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -946,22 +987,26 @@ gdf_error partition_hist(const gdf_column* col, PartGeom g, unsigned long long* 
 template <typename KT, bool KEEP_NULLS>
 gdf_error partition_scatter(const gdf_column* col, PartGeom g, const unsigned long long* h_cursors,
                             unsigned long long* d_cursors, KT* out_keys, int32_t* out_rows, const int32_t* payload,
-                            int32_t id_base, const PeerDst& peer) {
+                            int32_t id_base, const PeerDst& peer, const gdf_column* col2 = nullptr,
+                            uint32_t* out_k2 = nullptr) {
   const KT* keys = static_cast<const KT*>(col->data);
   const size_t n = col->size;
   B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
   static const bool prefetch = getenv("B200_SCATTER_PREFETCH") ? atoi(getenv("B200_SCATTER_PREFETCH")) != 0 : false;
-  auto kern = prefetch ? part_scatter_kernel<KT, KEEP_NULLS, true> : part_scatter_kernel<KT, KEEP_NULLS, false>;
-  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<KT>)));
+  auto kern = col2 ? part_scatter_kernel<KT, KEEP_NULLS, false, true>
+                   : (prefetch ? part_scatter_kernel<KT, KEEP_NULLS, true, false> : part_scatter_kernel<KT, KEEP_NULLS, false, false>);
+  const size_t smem_bytes = sizeof(ScatterSmem<KT>) + (col2 ? kScatterTile * sizeof(uint32_t) : 0);
+  ScatterK2 k2{col2 ? static_cast<const uint32_t*>(col2->data) : nullptr, col2 ? col2->valid : nullptr, out_k2};
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int per_sm = 1;
-  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, sizeof(ScatterSmem<KT>)));
+  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem_bytes));
   const size_t tiles = (n + kScatterTile - 1) / kScatterTile;
   const size_t cap = (size_t)sm_count() * (size_t)(per_sm > 0 ? per_sm : 1);  // exactly one resident wave
   const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
   {
     B200_TIMED("join_part_scatter");
-    kern<<<sblocks, kThreads, sizeof(ScatterSmem<KT>)>>>(keys, col->valid, n, g, d_cursors, out_keys, out_rows, payload,
-                                                        id_base, peer);
+    kern<<<sblocks, kThreads, smem_bytes>>>(keys, col->valid, n, g, d_cursors, out_keys, out_rows, payload, id_base, peer,
+                                            k2);
   }
   B200_CHECK_LAST();
   return GDF_SUCCESS;
@@ -971,8 +1016,9 @@ template <typename KT, bool KEEP_NULLS>
 gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, Scratch& rows_out,
                          unsigned long long* d_totals /*device [nparts]*/, unsigned long long* d_cursors,
                          unsigned long long* h_totals, size_t* kept, const int32_t* payload = nullptr,
-                         int32_t id_base = 0, KT* ext_keys = nullptr, int32_t* ext_rows = nullptr) {
-  gdf_error e = partition_hist<KT, KEEP_NULLS>(col, g, d_totals, h_totals);
+                         int32_t id_base = 0, KT* ext_keys = nullptr, int32_t* ext_rows = nullptr,
+                         const gdf_column* col2 = nullptr, Scratch* k2_out = nullptr) {
+  gdf_error e = partition_hist<KT, KEEP_NULLS>(col, g, d_totals, h_totals, col2);
   if (e != GDF_SUCCESS) return e;
   unsigned long long h_cursors[kMaxParts], run = 0;
   for (unsigned p = 0; p < g.nparts; ++p) {
@@ -988,7 +1034,13 @@ gdf_error partition_side(const gdf_column* col, PartGeom g, Scratch& keys_out, S
   }
   PeerDst none;
   none.on = 0;
-  return partition_scatter<KT, KEEP_NULLS>(col, g, h_cursors, d_cursors, ext_keys, ext_rows, payload, id_base, none);
+  uint32_t* k2_ptr = nullptr;
+  if (col2) {
+    B200_CUDA_TRY(k2_out->alloc((run ? run : 1) * sizeof(uint32_t)));
+    k2_ptr = k2_out->as<uint32_t>();
+  }
+  return partition_scatter<KT, KEEP_NULLS>(col, g, h_cursors, d_cursors, ext_keys, ext_rows, payload, id_base, none, col2,
+                                           k2_ptr);
 }
 
 gdf_error read_u64(const unsigned long long* d, unsigned long long* h) {
@@ -1050,7 +1102,7 @@ void view_indices(gdf_column* c, int32_t* data, size_t n) {
 template <typename KT>
 gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_column* build_col, bool flip,
                           gdf_column* out_l, gdf_column* out_r, bool* handled, const int32_t* probe_payload,
-                          const int32_t* build_payload) {
+                          const int32_t* build_payload, const gdf_column* probe_col2, const gdf_column* build_col2) {
   const size_t P = probe_col->size, B = build_col->size;
   const bool left_like = kind != JOIN_INNER;
   PartGeom g;
@@ -1080,26 +1132,32 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
 
   Scratch bkeys, brows, pkeys, prows;
   // unpartitioned pairs: row tag = position, or the caller's payload (then masks are not supported)
-  Pairs<KT> bp{static_cast<const KT*>(build_col->data), build_payload, build_col->valid, B};
-  Pairs<KT> pp{static_cast<const KT*>(probe_col->data), probe_payload, probe_col->valid, P};
+  Pairs<KT> bp{static_cast<const KT*>(build_col->data), build_payload, build_col->valid, B,
+               build_col2 ? static_cast<const uint32_t*>(build_col2->data) : nullptr, build_col2 ? build_col2->valid : nullptr};
+  Pairs<KT> pp{static_cast<const KT*>(probe_col->data), probe_payload, probe_col->valid, P,
+               probe_col2 ? static_cast<const uint32_t*>(probe_col2->data) : nullptr, probe_col2 ? probe_col2->valid : nullptr};
+  Scratch bk2, pk2;
   unsigned long long h_btot[kMaxParts];
   if (g.nparts > 1) {
     unsigned long long h_ptot[kMaxParts];
     size_t kept = 0;
-    gdf_error e = partition_side<KT, false>(build_col, g, bkeys, brows, d_totals, d_cursors, h_btot, &kept, build_payload);
+    gdf_error e = partition_side<KT, false>(build_col, g, bkeys, brows, d_totals, d_cursors, h_btot, &kept, build_payload, 0,
+                                            nullptr, nullptr, build_col2, &bk2);
     if (e != GDF_SUCCESS) return e;
-    bp = Pairs<KT>{bkeys.as<KT>(), brows.as<int32_t>(), nullptr, kept};
-    e = left_like ? partition_side<KT, true>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept, probe_payload)
-                  : partition_side<KT, false>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept, probe_payload);
+    bp = Pairs<KT>{bkeys.as<KT>(), brows.as<int32_t>(), nullptr, kept, build_col2 ? bk2.as<uint32_t>() : nullptr, nullptr};
+    e = left_like ? partition_side<KT, true>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept, probe_payload, 0,
+                                             nullptr, nullptr, probe_col2, &pk2)
+                  : partition_side<KT, false>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept, probe_payload, 0,
+                                              nullptr, nullptr, probe_col2, &pk2);
     if (e != GDF_SUCCESS) return e;
-    pp = Pairs<KT>{pkeys.as<KT>(), prows.as<int32_t>(), nullptr, kept};
+    pp = Pairs<KT>{pkeys.as<KT>(), prows.as<int32_t>(), nullptr, kept, probe_col2 ? pk2.as<uint32_t>() : nullptr, nullptr};
   } else {
     h_btot[0] = B;
   }
   // one table per partition, sized from the actual counts (load factor <= 0.5)
   unsigned long long h_toffset[kMaxParts], total_slots = 0;
   unsigned h_tmask[kMaxParts];
-  bool stream_ok = true;  // the streaming probe packs {partition, slot} into 8 + 24 bits
+  bool stream_ok = probe_col2 == nullptr;  // the streaming probe packs {partition, slot} into 8 + 24 bits; single keys only
   for (unsigned p = 0; p < g.nparts; ++p) {
     const unsigned slots = pow2_at_least(h_btot[p] ? 2 * h_btot[p] : 2);
     if (slots > (1u << 24)) stream_ok = false;
@@ -1129,6 +1187,7 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   }
   brows.release();  // build pairs are in the tables now
   bkeys.release();
+  bk2.release();
   const bool unique = h_flags[0] == 0;
   size_t bound = pp.n;
   gdf_error e = GDF_SUCCESS;
@@ -1188,13 +1247,18 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
 
 gdf_error partitioned_join(int kind, const gdf_column* probe_key, const gdf_column* build_key, bool flip,
                            gdf_column* out_l, gdf_column* out_r, bool* handled, const int32_t* probe_payload,
-                           const int32_t* build_payload) {
+                           const int32_t* build_payload, const gdf_column* probe_key2, const gdf_column* build_key2) {
+  // probe_key2 / build_key2: optional SECOND key column of 4-byte integers (composite keys such as C5's
+  // (int64,int32)); it rides in the slot's spare word.  Anything else goes to the generic path.
   *handled = false;
+  if (probe_key2 && !(probe_key2->dtype == GDF_INT32 || probe_key2->dtype == GDF_DATE32)) return GDF_SUCCESS;
   switch (probe_key->dtype) {
     case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
-      return run_partitioned<uint64_t>(kind, probe_key, build_key, flip, out_l, out_r, handled, probe_payload, build_payload);
+      return run_partitioned<uint64_t>(kind, probe_key, build_key, flip, out_l, out_r, handled, probe_payload, build_payload,
+                                       probe_key2, build_key2);
     case GDF_INT32: case GDF_DATE32:
-      return run_partitioned<uint32_t>(kind, probe_key, build_key, flip, out_l, out_r, handled, probe_payload, build_payload);
+      return run_partitioned<uint32_t>(kind, probe_key, build_key, flip, out_l, out_r, handled, probe_payload, build_payload,
+                                       probe_key2, build_key2);
     default: return GDF_SUCCESS;  // floats / narrow ints: generic path
   }
 }

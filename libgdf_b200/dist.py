@@ -87,7 +87,8 @@ class GdfOps(object):
         C, ffi, lib = self.C, self.ffi, self.lib
         n = key_cols[0].numel()
         out = torch.empty(n, dtype=torch.int8, device=key_cols[0].device)
-        cols = [C.Column(k, v) for k, v in zip(key_cols, valids)]
+        # null_count is not used by the kernels; passing it avoids Column()'s host-side popcount of the mask
+        cols = [C.Column(k, v, null_count=0 if v is None else 1) for k, v in zip(key_cols, valids)]
         lib.gdfx_rows_valid_to_bytes(C.column_array(cols), len(cols), ffi.cast("int8_t*", out.data_ptr()))
         return out
 
@@ -100,7 +101,7 @@ class GdfOps(object):
             n = keys[0].numel()
             mask = torch.empty((n + 7) // 8, dtype=torch.uint8, device=keys[0].device)
             lib.gdfx_bytes_to_valid(ffi.cast("int8_t*", ok.data_ptr()), n, ffi.cast("gdf_valid_type*", mask.data_ptr()))
-            return [C.Column(keys[0], mask)] + [C.Column(k) for k in keys[1:]]   # row-valid = AND over columns
+            return [C.Column(keys[0], mask, null_count=1)] + [C.Column(k) for k in keys[1:]]   # row-valid = AND over columns
 
         L, R = with_mask(lkeys, lok), with_mask(rkeys, rok)
         out_l, out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")

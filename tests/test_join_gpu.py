@@ -178,3 +178,30 @@ def test_error_codes():
     with pytest.raises(GDFError) as e:
         libgdf.gdf_inner_join(C.column_array([a]), 1, idx, C.column_array([a]), 1, idx, 1, 0, ffi.NULL, ffi.NULL, ffi.NULL, ctx)
     assert e.value.errcode == "GDF_DATASET_EMPTY"
+
+
+@pytest.mark.parametrize("kind", ["inner", "left", "full"])
+@pytest.mark.parametrize("key_types", [(np.int64, np.int32), (np.int32, np.int32)], ids=["i64-i32", "i32-i32"])
+def test_partitioned_path_composite_key_with_nulls(key_types, kind):
+    """(4/8-byte integer, 4-byte integer) composite keys take the radix-partitioned path with the second key in
+    the slot's spare word (C5's key shape).  Build side above the partitioning threshold, duplicate composite
+    keys, 30 % null rows with the null in either column."""
+    nl, nr = 3_000_000, 1_600_000
+    l = [np.random.randint(0, 900_000, nl).astype(key_types[0]), np.random.randint(0, 4, nl).astype(key_types[1])]
+    r = [np.random.randint(0, 900_000, nr).astype(key_types[0]), np.random.randint(0, 4, nr).astype(key_types[1])]
+
+    def masks(n):
+        null_rows, which = np.random.rand(n) < 0.3, np.random.rand(n) < 0.5
+        return [np.packbits(~(null_rows & which), bitorder="little"), np.packbits(~(null_rows & ~which), bitorder="little")]
+    check(kind, l, r, masks(nl), masks(nr))
+
+
+def test_partitioned_path_composite_key_same_first_key_different_second():
+    """Rows that agree on the first key column but not on the second must not match."""
+    nb = 1_300_000
+    b0 = np.random.permutation(nb).astype(np.int64)
+    build = [b0, np.zeros(nb, np.int32)]
+    probe = [b0[:2_000_000 % nb or nb].copy(), np.ones(min(2_000_000 % nb or nb, nb), np.int32)]
+    probe[1][::3] = 0                                              # every third probe row matches
+    check("inner", probe, build)
+    check("left", probe, build)
