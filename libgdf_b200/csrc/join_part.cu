@@ -328,7 +328,7 @@ struct Tables {
   const unsigned* mask;              // [nparts] slots_p - 1
 };
 
-template <typename KT>
+template <typename KT, bool K2>   // K2: composite key, second key in Pairs::k2 (kept out of the single-key code)
 __global__ void __launch_bounds__(kThreads)
 part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[0]=dup [1]=sentinel key*/) {
   // One CTA = one contiguous tile of pairs, tiles dispatched in index order: the pairs are
@@ -341,7 +341,7 @@ part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[
   const size_t tile_lo = (size_t)blockIdx.x * kBuildTile;
   unsigned long long key[U], prev[U];
   int32_t row[U];
-  uint32_t pad[U];
+  uint32_t pad[K2 ? U : 1];
   Slot* tab[U];
   unsigned s[U], mask[U];
   bool live[U];
@@ -351,19 +351,19 @@ part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[
     live[u] = i < b.n;
     key[u] = 0;
     row[u] = 0;
-    pad[u] = 0;
+    if (K2) pad[u] = 0;
     if (live[u]) {
       row[u] = b.rows ? b.rows[i] : (int32_t)i;
-      if (!b.rows && !(bit_valid(b.valid, i) && bit_valid(b.valid2, i))) live[u] = false;
+      if (!b.rows && !(bit_valid(b.valid, i) && (!K2 || bit_valid(b.valid2, i)))) live[u] = false;
       key[u] = (unsigned long long)b.keys[i];
-      if (b.k2) pad[u] = b.k2[i];
+      if (K2) pad[u] = b.k2[i];
     }
     if (live[u] && key[u] == kEmptyKey) {
       flags[1] = 1;
       live[u] = false;
     }
     uint32_t h = KeyBits<KT>::hash((KT)key[u]);
-    if (b.k2) h = with_k2(h, pad[u]);
+    if (K2) h = with_k2(h, pad[u]);
     const unsigned p = g.pid(h);
     tab[u] = t.slots + t.offset[p];
     mask[u] = t.mask[p];
@@ -385,7 +385,7 @@ part_build_kernel(Pairs<KT> b, PartGeom g, Tables t, int* __restrict__ flags /*[
       if (!((pend >> u) & 1u)) continue;
       if (prev[u] == kEmptyKey) {  // claimed
         tab[u][s[u]].row = row[u];
-        tab[u][s[u]].pad = (int32_t)pad[u];
+        if (K2) tab[u][s[u]].pad = (int32_t)pad[u];
         pend &= ~(1u << u);
       } else {
         if (prev[u] == key[u]) flags[0] = 1;  // duplicate build key
@@ -428,7 +428,7 @@ static __device__ __forceinline__ Slot ld_slot(const Slot* p) {
 
 // LEFT_LIKE: unmatched / NULL probe rows emit (row,-1).  UNIQUE: build keys are unique, stop at the
 // first match.  WRITE=false: count only.
-template <typename KT, bool LEFT_LIKE, bool UNIQUE, bool WRITE>
+template <typename KT, bool LEFT_LIKE, bool UNIQUE, bool WRITE, bool K2>
 __global__ void __launch_bounds__(kThreads)
 part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_probe,
                   int32_t* __restrict__ out_build, unsigned long long* __restrict__ cursor) {
@@ -438,13 +438,13 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
   unsigned long long key[kProbeRows];
   int32_t prow[kProbeRows], first[kProbeRows];
   unsigned cnt[kProbeRows], start[kProbeRows], mask[kProbeRows];
-  int32_t k2v[kProbeRows];
+  int32_t k2v[K2 ? kProbeRows : 1];
   const Slot* tab[kProbeRows];
   bool lookup[kProbeRows];
 #pragma unroll
   for (int i = 0; i < kProbeRows; ++i) {
     const size_t j = tile_base + (size_t)i * kThreads + threadIdx.x;
-    k2v[i] = 0;
+    if (K2) k2v[i] = 0;
     cnt[i] = 0;
     first[i] = -1;
     lookup[i] = false;
@@ -463,12 +463,12 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
         prow[i] = ok ? tag : ~tag;
       } else {
         prow[i] = (int32_t)j;
-        ok = bit_valid(pr.valid, j) && bit_valid(pr.valid2, j);
+        ok = bit_valid(pr.valid, j) && (!K2 || bit_valid(pr.valid2, j));
       }
-      if (pr.k2) k2v[i] = (int32_t)pr.k2[j];
+      if (K2) k2v[i] = (int32_t)pr.k2[j];
       if (ok && key[i] != kEmptyKey) {
         uint32_t h = KeyBits<KT>::hash(kraw);
-        if (pr.k2) h = with_k2(h, (uint32_t)k2v[i]);
+        if (K2) h = with_k2(h, (uint32_t)k2v[i]);
         const unsigned p = g.pid(h);
         tab[i] = t.slots + t.offset[p];
         mask[i] = t.mask[p];
@@ -492,7 +492,7 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
     unsigned s = start[i], c = 0;
     Slot cur = s0[i];
     while (cur.key != kEmptyKey) {
-      if (cur.key == key[i] && cur.pad == k2v[i]) {  // pad is 0 on both sides for single keys
+      if (cur.key == key[i] && (!K2 || cur.pad == k2v[i])) {
         if (c == 0) first[i] = cur.row;
         ++c;
         if (UNIQUE) break;
@@ -525,7 +525,7 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
       unsigned s = start[i];
       Slot cur = ld_slot(tab[i] + s);
       while (cur.key != kEmptyKey) {
-        if (cur.key == key[i] && cur.pad == k2v[i]) {
+        if (cur.key == key[i] && (!K2 || cur.pad == k2v[i])) {
           out_probe[pos] = prow[i];
           out_build[pos] = cur.row;
           ++pos;
@@ -1083,13 +1083,15 @@ gdf_error launch_probe(bool unique, bool write, const Pairs<KT>& pr, PartGeom g,
     return launch_probe_stream<KT, LEFT_LIKE, false, false>(pr, g, t, op, ob, cursor, ticket);
   }
   const unsigned tiles = (unsigned)((pr.n + kProbeTile - 1) / kProbeTile);
-  if (unique) {
-    if (write) part_probe_kernel<KT, LEFT_LIKE, true, true><<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
-    else part_probe_kernel<KT, LEFT_LIKE, true, false><<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
+  void (*kern)(Pairs<KT>, PartGeom, Tables, int32_t*, int32_t*, unsigned long long*) = nullptr;
+  if (pr.k2) {
+    kern = unique ? (write ? part_probe_kernel<KT, LEFT_LIKE, true, true, true> : part_probe_kernel<KT, LEFT_LIKE, true, false, true>)
+                  : (write ? part_probe_kernel<KT, LEFT_LIKE, false, true, true> : part_probe_kernel<KT, LEFT_LIKE, false, false, true>);
   } else {
-    if (write) part_probe_kernel<KT, LEFT_LIKE, false, true><<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
-    else part_probe_kernel<KT, LEFT_LIKE, false, false><<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
+    kern = unique ? (write ? part_probe_kernel<KT, LEFT_LIKE, true, true, false> : part_probe_kernel<KT, LEFT_LIKE, true, false, false>)
+                  : (write ? part_probe_kernel<KT, LEFT_LIKE, false, true, false> : part_probe_kernel<KT, LEFT_LIKE, false, false, false>);
   }
+  kern<<<tiles, kThreads>>>(pr, g, t, op, ob, cursor);
   B200_CHECK_LAST();
   return GDF_SUCCESS;
 }
@@ -1176,7 +1178,8 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   Tables t{table.as<Slot>(), d_toffset, d_tmask};
   if (bp.n) {
     B200_TIMED("join_part_build");
-    part_build_kernel<KT><<<(unsigned)((bp.n + kBuildTile - 1) / kBuildTile), kThreads>>>(bp, g, t, d_flags);
+    if (bp.k2) part_build_kernel<KT, true><<<(unsigned)((bp.n + kBuildTile - 1) / kBuildTile), kThreads>>>(bp, g, t, d_flags);
+    else part_build_kernel<KT, false><<<(unsigned)((bp.n + kBuildTile - 1) / kBuildTile), kThreads>>>(bp, g, t, d_flags);
     B200_CHECK_LAST();
   }
   int h_flags[2] = {0, 0};
