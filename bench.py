@@ -448,7 +448,12 @@ def bench_dist(args, rank, world, local_rank):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api = Api("b200")
     ops = D.GdfOps()
-    peer = D.PeerExchange(ops) if args.exchange == "p2p" else None
+    peer = None
+    if args.exchange == "p2p":
+        if D.PeerExchange.available(ops):
+            peer = D.PeerExchange(ops)
+        elif rank == 0:
+            print("bench.py: CUDA IPC peer mapping unavailable on this box, falling back to --exchange nccl", file=sys.stderr)
     peak_gbs, peak_kind = load_peak()
     clocks = Clocks(local_rank)
     P, B = int(1e9 * args.scale), int(1e8 * args.scale)
@@ -568,14 +573,28 @@ def bench_dist(args, rank, world, local_rank):
                                        % (12 * (P + B) / world * (world - 1) / world / 1e9)}
         if e2e:
             out["e2e"] = e2e
-        print(json.dumps(out))
+        emit(out)
     if peer:
         peer.close()
     dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints to fd 1
+    (e.g. NCCL's "NCCL version ..." banner) has been redirected to stderr by main()."""
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -597,7 +616,7 @@ def main():
     try:
         api = Api(args.impl)
     except Exception as exc:  # reference library not built
-        print(json.dumps({"impl": args.impl, "unavailable": str(exc)}))
+        emit({"impl": args.impl, "unavailable": str(exc)})
         return 0
     only = set(filter(None, args.only.split(",")))
     clocks = Clocks(local_rank)
@@ -684,7 +703,7 @@ def main():
             out["cpu_baseline"] = cpu_baseline_join(args.scale)
         except Exception as exc:
             out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "port", "sample": "failed: %s" % exc}
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 

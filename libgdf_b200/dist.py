@@ -225,6 +225,39 @@ class PeerExchange(object):
         self.slots = {}   # name -> {"cap", "itemsize", "mine": (kptr, iptr), "peers": ([kptr..], [iptr..])}
         self._flag = None
 
+    @staticmethod
+    def available(ops, group=None):
+        """Collective self-test: can every rank map every other rank's memory (CUDA IPC + peer access)?
+        All ranks get the same answer, so callers can fall back to the NCCL exchange together."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ok, opened, ptr = 1, [], None
+        try:
+            ptr, handle = ops.peer_alloc(256)
+        except Exception:
+            ok, handle = 0, b""
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        if ok:
+            try:
+                for r, h in enumerate(handles):
+                    if r != rank:
+                        if len(h) != 64:
+                            raise RuntimeError("peer %d has no handle" % r)
+                        opened.append(ops.peer_open(h))
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        for p in opened:
+            try:
+                ops.peer_close(p)
+            except Exception:
+                pass
+        dist.barrier(group=group)
+        if ptr is not None:
+            ops.peer_free(ptr)
+        return bool(flag.item())
+
     def _ensure(self, name, rows, itemsize):
         slot = self.slots.get(name)
         if slot and slot["cap"] >= rows and slot["itemsize"] == itemsize:
