@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""Benchmark of the gdf hot path on B200 (see DESIGN.md "Measurement").
+"""Benchmark of the gdf hot path on B200.
 
-One JSON line on stdout.  Headline workload (BASELINE.json metric "rows/sec hash inner-join ... int64"):
-C3 = gdf_inner_join of 1e9 probe rows x 1e8 build rows, int64 keys (build = permutation, probe
-uniform, every probe row matches once).  A "step" is one gdf_inner_join call over device-resident
-columns, outputs freed with gdf_column_free.  The same line carries the other two single-GPU
-configs as `workloads` entries: C4 gdf_group_by_sum (1e9 rows, 1e6 int64 groups, Zipf s=1.05) and
-C2 gdf_filter (1e9 int64 rows, 10 % selectivity), each with its own roofline object.
+Exactly ONE JSON line on stdout (anything a library prints to fd 1 is diverted to stderr).
 
-  value      rows/s (probe+build rows per step / device time), inputs resident in HBM
-  e2e        same metric through the same C-ABI call but from pinned HOST buffers: H2D of both key
-             columns and D2H of both index columns inside the timed region
-  roofline   dominant kernel of the headline step: algorithmic bytes of that kernel / its average
-             launch duration (CUDA events recorded by the library around each launch, live in the
-             timed steps) vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the C oracle port (single thread) on a bounded sample of the same workload
-
---impl reference runs the reference's own kernels (oracle/_ref/libgdf_ref.so = gpuopenanalytics/libgdf
-rebuilt for sm_100a; the reference has no CPU implementation) through the identical harness.
+N = 1   headline = BASELINE.json's metric "rows/sec hash inner-join ... int64": C3 = gdf_inner_join of 1e9
+        probe rows x 1e8 build rows, int64 keys (build = permutation, probe uniform, every probe row matches
+        once).  A step = one gdf_inner_join call over device-resident columns + gdf_column_free of its outputs.
+        The same line carries C4 gdf_group_by_sum (1e9 rows, 1e6 int64 groups, Zipf s=1.05) and C2 gdf_filter
+        (1e9 int64 rows, 10 % selectivity) under `workloads`, each with its own roofline object.
+  value      rows/s (probe+build rows per step / CUDA-event time), inputs resident in HBM
+  e2e        the same C-ABI call from pinned HOST buffers: H2D of both key columns and D2H of both index
+             columns inside the timed region (PCIe-bound)
+  roofline   dominant kernel of the headline step: algorithmic bytes of that kernel / its average launch
+             duration (CUDA events recorded by the library around every launch, live in the timed steps)
+             vs MEASURED_PEAKS.json hbm_gbs; traffic = DRAM bytes per launch from the committed full-size
+             ncu capture (profiles/r01c_traffic_full_size.json)
+  cpu_baseline  the C oracle port (single thread) on a bounded sample of C3
+N > 1   (torchrun) strong scaling of C3: the two tables are block-distributed over the ranks; every step
+        partitions both sides by destination rank INSIDE one kernel that stores the rows into the peers'
+        receive buffers over NVLink (--exchange p2p, default; falls back to hash-partition + NCCL all_to_all
+        when CUDA IPC peer mapping is unavailable, or with --exchange nccl), then joins locally.  Time = max
+        over ranks of the CUDA-event time between two barriers.
+--impl reference   the reference's own kernels (oracle/_ref/libgdf_ref.so = gpuopenanalytics/libgdf rebuilt for
+        sm_100a; the reference is a CUDA library and has no CPU implementation) through the identical harness
+        on a bounded sample (1/10 of the rows; 5e6 rows for its group-by, whose CAS loop serialises on the
+        Zipf hot key).  Under torchrun only rank 0 runs it.
 """
 import argparse
 import json

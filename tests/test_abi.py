@@ -24,6 +24,17 @@ def test_libgdf_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_libgdf_exports_every_extension_symbol():
+    """include/gdf_b200_ext.h: measurement hooks and the multi-GPU layer's entry points (not in the reference)."""
+    import libgdf_b200
+    lib = ctypes.CDLL(libgdf_b200.lib_path("libgdf.so"))
+    names = _declared("gdf_b200_ext.h")
+    assert {"gdfx_profile_enable", "gdfx_partition_pairs", "gdfx_join_pairs", "gdfx_partition_scatter_peer",
+            "gdfx_peer_alloc", "gdfx_rows_valid_to_bytes"} <= set(names)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
 def test_librmm_exports_every_declared_symbol():
     import libgdf_b200
     lib = ctypes.CDLL(libgdf_b200.lib_path("librmm.so"))
