@@ -424,10 +424,10 @@ def roofline_for(res, wl, peak_gbs, peak_kind, scale=1.0):
 
 
 def cpu_baseline_join(scale):
-    """C oracle port (oracle/gdf_oracle.c, single thread) on a bounded sample of C3: 2e7 x 2e6."""
+    """C oracle port (oracle/gdf_oracle.c, single thread) on a bounded sample of C3: 5e7 x 5e6 (~10 s)."""
     import oracle
     rng = np.random.RandomState(SEED % (2 ** 32))
-    B, P = max(int(2e6 * min(scale * 10, 1.0)), 1000), max(int(2e7 * min(scale * 10, 1.0)), 10000)
+    B, P = max(int(5e6 * min(scale * 10, 1.0)), 1000), max(int(5e7 * min(scale * 10, 1.0)), 10000)
     build = rng.permutation(B).astype(np.int64)
     probe = rng.randint(0, B, P).astype(np.int64)
     t0 = time.perf_counter()
@@ -587,6 +587,41 @@ def bench_dist(args, rank, world, local_rank):
     return 0
 
 
+def cpu_baseline_pyarrow(scale):
+    """pyarrow CPU pass over the same kind of Arrow columns on all host cores, bounded samples
+    (join 2e7 x 2e6, group-by 2e7 rows / 2e4 Zipf groups, filter 2e7 rows).  Reported, not a target."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    pa.set_cpu_count(os.cpu_count() or 1)
+    rng = np.random.RandomState(SEED % (2 ** 32))
+    f = min(scale * 10, 1.0)
+    B, P = max(int(2e6 * f), 1000), max(int(2e7 * f), 10000)
+    out = {"cores": pa.cpu_count(), "unit": "rows/s", "pyarrow": pa.__version__}
+    build, probe = rng.permutation(B).astype(np.int64), rng.randint(0, B, P).astype(np.int64)
+    lt = pa.table({"k": probe, "l": np.arange(P, dtype=np.int32)})
+    rt = pa.table({"k": build, "r": np.arange(B, dtype=np.int32)})
+    t0 = time.perf_counter()
+    j = lt.join(rt, keys="k", join_type="inner")
+    dt = time.perf_counter() - t0
+    assert j.num_rows == P
+    out["join"] = {"value": (P + B) / dt, "sample": "Table.join inner, %d x %d int64 keys, %.2f s" % (P, B, dt)}
+    G = max(int(2e4 * f), 16)
+    w = np.arange(1, G + 1, dtype=np.float64) ** -1.05
+    keys = (rng.choice(G, size=P, p=w / w.sum()).astype(np.int64)) * 7919 + 13
+    vals = rng.randint(0, 1000, P).astype(np.int64)
+    t0 = time.perf_counter()
+    g = pa.table({"k": keys, "v": vals}).group_by("k").aggregate([("v", "sum")])
+    dt = time.perf_counter() - t0
+    assert g.num_rows <= G
+    out["groupby"] = {"value": P / dt, "sample": "group_by().aggregate(sum), %d rows, %d Zipf groups, %.2f s" % (P, G, dt)}
+    col = pa.array(rng.randint(0, 10, P).astype(np.int64))
+    t0 = time.perf_counter()
+    idx = pc.indices_nonzero(pc.equal(col, 3))
+    dt = time.perf_counter() - t0
+    out["filter"] = {"value": P / dt, "sample": "indices_nonzero(equal(col, 3)), %d rows, %d selected, %.3f s" % (P, len(idx), dt)}
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -710,6 +745,10 @@ def main():
             out["cpu_baseline"] = cpu_baseline_join(args.scale)
         except Exception as exc:
             out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "port", "sample": "failed: %s" % exc}
+        try:
+            out["cpu_baseline_pyarrow"] = cpu_baseline_pyarrow(args.scale)
+        except Exception as exc:
+            out["cpu_baseline_pyarrow"] = {"error": str(exc)[:200]}
     emit(out)
     return 0
 
