@@ -264,6 +264,7 @@ class JoinWorkload(object):
         return 8 * (self.P + self.B), 8 * self.P
 
     def e2e_step(self):
+        """One host-to-host join through one C-ABI call: H2D both key columns, gdf_inner_join, D2H both index columns."""
         self.d_probe.copy_(self.h_probe, non_blocking=True)
         self.d_build.copy_(self.h_build, non_blocking=True)
         self.call(self.d_probe, self.d_build)
@@ -272,6 +273,69 @@ class JoinWorkload(object):
         self.h_out_r[:n].copy_(alias(self.api.ffi, self.out_r.data, n, np.int32), non_blocking=True)
         torch.cuda.synchronize()
         self.free()
+        self.e2e_pairs = n
+
+    def e2e_step_pipelined(self, chunks=8):
+        """The same host-to-host join the way a caller streams a big probe table through the C ABI: the probe
+        column goes up in `chunks` pieces on a copy stream, gdf_inner_join runs per piece against the resident
+        build column (default stream), and each piece's index pairs (left ids rebased to the whole table) go
+        down on a second copy stream - so H2D, the join and D2H overlap and PCIe is used in both directions at
+        once.  Same bytes, same result set as e2e_step (pair order is unspecified in both)."""
+        ffi, lib = self.api.ffi, self.api.lib
+        P = self.P
+        per = ((P + chunks - 1) // chunks + 1) & ~1          # even: 16-byte aligned int64 slices
+        if per < self.B:                                       # keep the build side on the right (no INNER flip)
+            return self.e2e_step()
+        if not hasattr(self, "s_in"):
+            self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        bounds = [(lo, min(P, lo + per)) for lo in range(0, P, per)]
+        with torch.cuda.stream(self.s_in):
+            self.d_build.copy_(self.h_build, non_blocking=True)
+            ready = []
+            for lo, hi in bounds:
+                self.d_probe[lo:hi].copy_(self.h_probe[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.s_in)
+                ready.append(ev)
+        total, inflight = 0, []
+        for (lo, hi), ev in zip(bounds, ready):
+            cur.wait_event(ev)
+            out_l, out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
+            lc, rc = self.api.column(self.d_probe[lo:hi]), self.api.column(self.d_build)
+            la, ra = ffi.new("gdf_column*[]", [lc]), ffi.new("gdf_column*[]", [rc])
+            self.api.check(lib.gdf_inner_join(la, 1, self.idx, ra, 1, self.idx, 1, 0, ffi.NULL, out_l, out_r, self.ctx),
+                           "gdf_inner_join")
+            n = int(out_l.size)
+            if n:
+                l, r = alias(ffi, out_l.data, n, np.int32), alias(ffi, out_r.data, n, np.int32)
+                if lo:
+                    l.add_(lo)                                 # piece-relative -> table-relative left row ids
+                done = torch.cuda.Event()
+                done.record(cur)
+                self.s_out.wait_event(done)
+                with torch.cuda.stream(self.s_out):
+                    self.h_out_l[total:total + n].copy_(l, non_blocking=True)
+                    self.h_out_r[total:total + n].copy_(r, non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(self.s_out)
+                inflight.append((copied, out_l, out_r))
+                total += n
+            while len(inflight) > 2:                           # free a piece's outputs once its D2H has finished
+                copied, a, b = inflight.pop(0)
+                copied.synchronize()
+                lib.gdf_column_free(a)
+                lib.gdf_column_free(b)
+        torch.cuda.synchronize()
+        for _, a, b in inflight:
+            lib.gdf_column_free(a)
+            lib.gdf_column_free(b)
+        self.e2e_pairs = total
+
+    def e2e_verify(self):
+        """Host-side check of the last e2e result: pair count and the left ids form a permutation of the probe rows."""
+        n = self.e2e_pairs
+        return n == self.P and int(self.h_out_l[:n].numpy().sum(dtype=np.int64)) == self.P * (self.P - 1) // 2
 
 
 class GroupbyWorkload(object):
@@ -685,11 +749,25 @@ def main():
         if not args.no_e2e and args.impl == "b200":
             try:
                 h2d, d2h = wl.e2e_setup()
-                e_ms, _ = timed_steps(wl.e2e_step, 1, max(1, min(args.steps, 3)))
+                e_steps = max(1, min(args.steps, 3))
+                e_ms, _ = timed_steps(wl.e2e_step, 1, e_steps)
                 out["e2e"] = {"value": wl.rows_per_step / (e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": h2d,
-                              "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "steps": max(1, min(args.steps, 3))}
+                              "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "steps": e_steps, "mode": "one call",
+                              "result_ok": wl.e2e_verify()}
+                try:   # streamed through the same C-ABI call in 8 probe pieces: copies overlap the joins
+                    p_ms, _ = timed_steps(wl.e2e_step_pipelined, 1, e_steps)
+                    if wl.e2e_verify() and p_ms < e_ms:
+                        out["e2e"].update({"one_call_ms_per_step": e_ms, "one_call_value": out["e2e"]["value"],
+                                           "value": wl.rows_per_step / (p_ms * 1e-3), "ms_per_step": p_ms,
+                                           "mode": "probe column streamed in 8 pieces, one gdf_inner_join per piece, "
+                                                   "H2D / join / D2H overlapped on three streams", "result_ok": True})
+                    else:
+                        out["e2e"]["pipelined_ms_per_step"] = p_ms
+                except Exception as exc:
+                    out["e2e"]["pipelined_error"] = str(exc)[:200]
                 for a in ("h_probe", "h_build", "d_probe", "d_build", "h_out_l", "h_out_r"):
                     delattr(wl, a)
+                torch.cuda.synchronize()
             except Exception as exc:
                 out["e2e"] = {"value": None, "unit": "rows/s", "error": str(exc)[:200]}
         workloads["join"] = res
