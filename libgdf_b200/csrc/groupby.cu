@@ -544,6 +544,10 @@ gdf_error group_by_single(int ncols, gdf_column** cols, gdf_column* col_agg, gdf
     return GDF_SUCCESS;
   }
   if (ctxt->flag_method != GDF_HASH) return GDF_UNSUPPORTED_METHOD;  // sort-based group-by: see DESIGN.md
+  // The reference sorts the hash group-by's output by key when flag_sort_result is set
+  // (groupby_compute_api.h:211-222).  That sort is not implemented yet: refuse loudly instead of handing back
+  // groups in unspecified order to a caller that asked for a sorted result.
+  if (ctxt->flag_sort_result == 1) return GDF_UNSUPPORTED_METHOD;
   gdf_nvtx_range_push("LIBGDF_GROUPBY", GDF_GREEN);
   gdf_error e = group_by_hash(ncols, cols, col_agg, out_col_values, out_col_agg, op, ctxt->flag_sort_result == 1);
   gdf_nvtx_range_pop();

@@ -90,6 +90,10 @@ def test_groupby_validation(h, fn):
     sort_ctx = h.ffi.new("gdf_context*")
     h.lib.gdf_context_view(sort_ctx, 0, h.lib.GDF_SORT, 0, 0, 0)
     assert code(h, f, 1, h.arr([k]), v, h.ffi.NULL, h.arr([ok]), ov, sort_ctx) == "GDF_UNSUPPORTED_METHOD"
+    # a sorted result (flag_sort_result) is not implemented yet: refused, not silently ignored
+    sorted_ctx = h.ffi.new("gdf_context*")
+    h.lib.gdf_context_view(sorted_ctx, 0, h.lib.GDF_HASH, 0, 1, 0)
+    assert code(h, f, 1, h.arr([k]), v, h.ffi.NULL, h.arr([ok]), ov, sorted_ctx) == "GDF_UNSUPPORTED_METHOD"
 
 
 def test_filter_comparison_stencil_validation(h):
