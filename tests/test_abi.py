@@ -127,3 +127,14 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_reference_package_names_resolve_after_install_aliases():
+    """INTEGRATION.md route (a): unmodified reference-side imports find the drop-in bindings."""
+    import libgdf_b200
+    libgdf_b200.install_aliases()
+    from libgdf_cffi import ffi, libgdf, GDFError          # noqa: F401  (the reference's import line)
+    from librmm_cffi import librmm, librmm_config           # noqa: F401
+    assert libgdf.gdf_column_sizeof() == ffi.sizeof("gdf_column") == 56
+    for name in ("initialize", "finalize", "to_device", "device_array", "device_array_like", "csv_log"):
+        assert hasattr(librmm, name)
