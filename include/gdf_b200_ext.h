@@ -10,6 +10,14 @@
 int gdfx_profile_enable(int on);
 size_t gdfx_profile_report(char *buf, size_t capacity);
 
+/* Library-internal scratch memory (hash tables, partition buffers) is cached between calls so that warm calls
+ * never enter the driver (csrc/block_cache.h).  The cache is bounded (default: half of the device's memory) and is
+ * handed back automatically when one of the library's own allocations runs out of memory; a caller that shares
+ * the GPU with other allocators can also empty it (returns the bytes released), inspect it, or bound it. */
+size_t gdfx_trim_scratch(void);
+size_t gdfx_scratch_cached_bytes(void);
+void gdfx_set_scratch_limit(size_t bytes);
+
 /* Multi-GPU layer helper (libgdf_b200/dist.py): indices[i] = payload[indices[i]] in place for every
  * non-negative entry (< payload_rows), -1 otherwise.  `indices` is a GDF_INT32 join output column;
  * `payload` is a device array of the global row ids that travelled with the exchanged keys. */

@@ -57,14 +57,19 @@ inline size_t valid_bytes(size_t rows) { return (rows + 7) / 8; }  // ref includ
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ----------------------------------------------------------------------------------------------
-// Stream-ordered scratch.  Library-internal temporaries (hash tables, partition buffers, look-back
-// descriptors) come from the device's default cudaMallocAsync pool with an unbounded release
-// threshold: after the first call of a given size, allocation is a pointer bump with no device
-// synchronisation.  Library-OWNED OUTPUTS (join index columns) go through rmmAlloc instead, because
+// Scratch.  Library-internal temporaries (hash tables, partition buffers, look-back descriptors) come from a
+// caching block allocator (block_cache.h): a freed block is kept and handed back for the next request of about
+// the same size, so after the first call of a given shape allocation never enters the driver and no API call
+// pays a cudaMalloc/cudaFree device synchronisation.  The cache is bounded (half of the device's memory by
+// default, gdfx_set_scratch_limit), is handed back to the driver when any allocation of this library or of
+// librmm's pool runs out of memory, and can be emptied by the caller (gdfx_trim_scratch).  Everything the library
+// launches runs on the legacy default stream, so reuse is ordered by that stream.
+// Library-OWNED OUTPUTS (join index columns, result_cols) go through rmmAlloc instead (output_alloc), because
 // the caller releases them with gdf_column_free -> rmmFree (ref src/column.cpp:222-227).
 // ----------------------------------------------------------------------------------------------
 cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s);
 cudaError_t scratch_free(void* p, cudaStream_t s);
+rmmError_t output_alloc(void** p, size_t bytes);  // rmmAlloc(stream 0); trims the scratch cache and retries on failure
 
 struct Scratch {  // RAII wrapper; frees in stream order
   void* ptr = nullptr;

@@ -28,6 +28,7 @@
 //   * single 4/8-byte integer key columns take the radix-partitioned path of join_part.cuh so that
 //     every table probe is an L2 hit instead of a DRAM row miss.
 #include <cstring>
+#include <vector>
 
 #include "select.cuh"
 #include "table.cuh"
@@ -244,8 +245,8 @@ gdf_error read_u64(const unsigned long long* d, unsigned long long* h) {
 
 gdf_error alloc_index_pair(size_t capacity, int32_t** a, int32_t** b) {
   *a = *b = nullptr;
-  B200_RMM_TRY(rmmAlloc((void**)a, (capacity ? capacity : 1) * sizeof(int32_t), 0));
-  if (rmmAlloc((void**)b, (capacity ? capacity : 1) * sizeof(int32_t), 0) != RMM_SUCCESS) {
+  B200_RMM_TRY(output_alloc((void**)a, (capacity ? capacity : 1) * sizeof(int32_t)));
+  if (output_alloc((void**)b, (capacity ? capacity : 1) * sizeof(int32_t)) != RMM_SUCCESS) {
     rmmFree(*a, 0);
     *a = nullptr;
     return GDF_MEMORYMANAGER_ERROR;
@@ -490,8 +491,12 @@ gdf_error alloc_result_col(gdf_column* out, size_t n, gdf_dtype dtype) {
   gdf_column_view(out, nullptr, nullptr, n, dtype);
   const int w = dtype_width(dtype);
   B200_REQUIRE(w != 0, GDF_UNSUPPORTED_DTYPE);
-  B200_RMM_TRY(rmmAlloc(&out->data, (n ? n : 1) * (size_t)w, 0));
-  B200_RMM_TRY(rmmAlloc((void**)&out->valid, valid_bytes(n) ? valid_bytes(n) : 1, 0));
+  B200_RMM_TRY(output_alloc(&out->data, (n ? n : 1) * (size_t)w));
+  if (output_alloc((void**)&out->valid, valid_bytes(n) ? valid_bytes(n) : 1) != RMM_SUCCESS) {
+    rmmFree(out->data, 0);
+    out->data = nullptr;
+    return GDF_MEMORYMANAGER_ERROR;
+  }
   B200_CUDA_TRY(cudaMemsetAsync(out->valid, 0, valid_bytes(n), 0));
   return GDF_SUCCESS;
 }
@@ -506,16 +511,29 @@ gdf_error construct_join_output(int kind, gdf_column** left_cols, int num_left_c
       if (set[i] == idx) return true;
     return false;
   };
-  gdf_column* lnon[256];
-  gdf_column* rnon[256];
-  int nl = 0, nr = 0;
-  for (int i = 0; i < num_left_cols && nl < 256; ++i)
-    if (!is_join_col(left_join_cols, i)) lnon[nl++] = left_cols[i];
-  for (int i = 0; i < num_right_cols && nr < 256; ++i)
-    if (!is_join_col(right_join_cols, i)) rnon[nr++] = right_cols[i];
+  std::vector<gdf_column*> lnon, rnon;
+  for (int i = 0; i < num_left_cols; ++i)
+    if (!is_join_col(left_join_cols, i)) lnon.push_back(left_cols[i]);
+  for (int i = 0; i < num_right_cols; ++i)
+    if (!is_join_col(right_join_cols, i)) rnon.push_back(right_cols[i]);
+  const int nl = (int)lnon.size(), nr = (int)rnon.size();
+  // layout [left non-key.., key.., right non-key..] (ref joining.cu:412-439): the caller's counts must describe
+  // exactly that - duplicate join indices or a wrong result_num_cols would otherwise index past the lists
+  if (result_num_cols != nl + num_cols_to_join + nr) {
+    gdf_nvtx_range_pop();
+    return GDF_INVALID_API_CALL;
+  }
   const size_t n = left_indices->size;
-  const int left_end = num_left_cols - num_cols_to_join;
-  const int right_begin = num_left_cols;
+  const int left_end = nl;
+  const int right_begin = nl + num_cols_to_join;
+  for (int i = 0; i < result_num_cols; ++i) {
+    if (result_cols[i] == nullptr) {
+      gdf_nvtx_range_pop();
+      return GDF_DATASET_EMPTY;
+    }
+    result_cols[i]->data = nullptr;
+    result_cols[i]->valid = nullptr;
+  }
   gdf_error e = GDF_SUCCESS;
   for (int i = 0; i < left_end && e == GDF_SUCCESS; ++i) e = alloc_result_col(result_cols[i], n, lnon[i]->dtype);
   for (int i = right_begin; i < result_num_cols && e == GDF_SUCCESS; ++i)
@@ -527,13 +545,21 @@ gdf_error construct_join_output(int kind, gdf_column** left_cols, int num_left_c
     rjoin[j] = right_cols[right_join_cols[j]];
     e = alloc_result_col(result_cols[left_end + j], n, ljoin[j]->dtype);
   }
-  if (e == GDF_SUCCESS && nl) e = gather_columns(lnon, result_cols, nl, left_indices, false);
-  if (e == GDF_SUCCESS && nr) e = gather_columns(rnon, result_cols + right_begin, nr, right_indices, false);
+  if (e == GDF_SUCCESS && nl) e = gather_columns(lnon.data(), result_cols, nl, left_indices, false);
+  if (e == GDF_SUCCESS && nr) e = gather_columns(rnon.data(), result_cols + right_begin, nr, right_indices, false);
   if (e == GDF_SUCCESS && num_cols_to_join) {
     // key columns: FULL first takes the right side's keys, then the left side overwrites where it has a row
     if (kind == JOIN_FULL) e = gather_columns(rjoin, result_cols + left_end, num_cols_to_join, right_indices, false);
     if (e == GDF_SUCCESS)
       e = gather_columns(ljoin, result_cols + left_end, num_cols_to_join, left_indices, kind == JOIN_FULL);
+  }
+  if (e != GDF_SUCCESS) {  // hand back whatever was allocated before the failure
+    for (int i = 0; i < result_num_cols; ++i) {
+      rmmFree(result_cols[i]->data, 0);
+      rmmFree(result_cols[i]->valid, 0);
+      result_cols[i]->data = nullptr;
+      result_cols[i]->valid = nullptr;
+    }
   }
   gdf_nvtx_range_pop();
   return e;

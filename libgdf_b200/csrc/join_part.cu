@@ -1211,8 +1211,8 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
     return GDF_SUCCESS;
   }
   int32_t *op = nullptr, *ob = nullptr;
-  B200_RMM_TRY(rmmAlloc((void**)&op, capacity * sizeof(int32_t), 0));
-  if (rmmAlloc((void**)&ob, capacity * sizeof(int32_t), 0) != RMM_SUCCESS) {
+  B200_RMM_TRY(output_alloc((void**)&op, capacity * sizeof(int32_t)));
+  if (output_alloc((void**)&ob, capacity * sizeof(int32_t)) != RMM_SUCCESS) {
     rmmFree(op, 0);
     return GDF_MEMORYMANAGER_ERROR;
   }

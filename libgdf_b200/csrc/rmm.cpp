@@ -8,6 +8,9 @@
 //                               back for the next request of about the same size, so warm operator
 //                               calls never enter the driver - the property cnmem gives the
 //                               reference.  An initial_pool_size > 0 pre-warms one block of that size.
+//                               Reuse is stream-aware like cnmem's per-stream child pools: a block freed on
+//                               stream A goes to a later request on A at once and to a request on another
+//                               stream only behind an event recorded on A at free time.
 // A pointer from either mode may be released in either mode (rmmFree falls back to cudaFree for
 // pointers the cache does not own), so changing mode between alloc and free is safe.
 // The optional event log keeps the reference's CSV schema (memory_manager.cpp:46-64).
@@ -64,7 +67,7 @@ rmmError_t from_cuda(cudaError_t e) {
 }
 
 b200::BlockCache& pool() {
-  static b200::BlockCache* c = new b200::BlockCache();  // leaked on purpose (exit-order safety)
+  static b200::BlockCache* c = new b200::BlockCache(/*track_streams=*/true);  // leaked on purpose (exit-order safety)
   return *c;
 }
 
@@ -152,7 +155,7 @@ rmmError_t rmmAlloc(void** ptr, size_t size, cudaStream_t stream) {
   if (!ptr && !size) return RMM_SUCCESS;
   if (!ptr) return RMM_ERROR_INVALID_ARGUMENT;
   LogScope log(0, nullptr, size, stream);
-  const cudaError_t e = pool_mode() ? pool().alloc(ptr, size) : cudaMalloc(ptr, size);
+  const cudaError_t e = pool_mode() ? pool().alloc(ptr, size, stream) : cudaMalloc(ptr, size);
   if (e != cudaSuccess) return from_cuda(e);
   log.ptr = *ptr;
   return RMM_SUCCESS;
@@ -161,7 +164,7 @@ rmmError_t rmmAlloc(void** ptr, size_t size, cudaStream_t stream) {
 rmmError_t rmmFree(void* ptr, cudaStream_t stream) {
   LogScope log(2, ptr, 0, stream);
   if (!ptr) return RMM_SUCCESS;  // cudaFree(nullptr) is a no-op in the reference as well
-  if (pool().release(ptr)) return RMM_SUCCESS;  // block came from the cache (whatever the mode is now)
+  if (pool().release(ptr, stream)) return RMM_SUCCESS;  // block came from the cache (whatever the mode is now)
   return from_cuda(cudaFree(ptr));
 }
 
@@ -172,10 +175,10 @@ rmmError_t rmmRealloc(void** ptr, size_t new_size, cudaStream_t stream) {
   if (!ptr) return RMM_ERROR_INVALID_ARGUMENT;
   LogScope log(1, nullptr, new_size, stream);
   rmmError_t r = RMM_SUCCESS;
-  if (*ptr && !pool().release(*ptr)) {
+  if (*ptr && !pool().release(*ptr, stream)) {
     if ((r = from_cuda(cudaFree(*ptr))) != RMM_SUCCESS) return r;
   }
-  const cudaError_t e = pool_mode() ? pool().alloc(ptr, new_size) : cudaMalloc(ptr, new_size);
+  const cudaError_t e = pool_mode() ? pool().alloc(ptr, new_size, stream) : cudaMalloc(ptr, new_size);
   if ((r = from_cuda(e)) != RMM_SUCCESS) return r;
   log.ptr = *ptr;
   return RMM_SUCCESS;
@@ -200,6 +203,11 @@ rmmError_t rmmGetInfo(size_t* freeSize, size_t* totalSize, cudaStream_t /*stream
   if (!freeSize || !totalSize) return RMM_ERROR_INVALID_ARGUMENT;
   return from_cuda(cudaMemGetInfo(freeSize, totalSize));
 }
+
+// Extension (not in the reference ABI): give every cached pool block back to the driver.  libgdf.so calls it
+// before it reports an out-of-memory condition for its own scratch.
+void rmmxTrimPool() { pool().trim(); }
+size_t rmmxPoolCachedBytes() { return pool().cached_bytes(); }
 
 rmmError_t rmmWriteLog(const char* filename) {
   if (!filename) return RMM_ERROR_INVALID_ARGUMENT;

@@ -32,9 +32,32 @@ static BlockCache& scratch_cache() {
   static BlockCache* c = new BlockCache();  // leaked on purpose: no teardown-order issues at exit
   return *c;
 }
-cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t /*s*/) { return scratch_cache().alloc(p, bytes); }
+extern "C" void rmmxTrimPool();  // librmm.so (rmm.cpp)
+
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t /*s*/) {
+  cudaError_t e = scratch_cache().alloc(p, bytes);  // trims its own cache and retries on out-of-memory
+  if (e == cudaErrorMemoryAllocation) {             // still no room: blocks parked in the rmm pool are the other candidate
+    cudaGetLastError();
+    rmmxTrimPool();
+    e = scratch_cache().alloc(p, bytes);
+  }
+  return e;
+}
 cudaError_t scratch_free(void* p, cudaStream_t /*s*/) {
   return scratch_cache().release(p) ? cudaSuccess : cudaFree(p);
+}
+
+// Library-owned outputs (join index columns, result_cols): rmmAlloc on the default stream.  In rmm's default mode
+// that is a plain cudaMalloc, which can fail while gigabytes sit in this library's scratch cache - so on failure
+// the cache is handed back to the driver and the request repeated once.
+rmmError_t output_alloc(void** p, size_t bytes) {
+  rmmError_t r = rmmAlloc(p, bytes, 0);
+  if (r == RMM_ERROR_OUT_OF_MEMORY || r == RMM_ERROR_CUDA_ERROR) {
+    cudaGetLastError();
+    scratch_cache().trim();
+    r = rmmAlloc(p, bytes, 0);
+  }
+  return r;
 }
 
 void* pinned_mailbox() {
@@ -92,6 +115,14 @@ KernelTimer::~KernelTimer() {
 }
 
 }  // namespace b200
+
+extern "C" size_t gdfx_trim_scratch() {
+  const size_t had = b200::scratch_cache().cached_bytes();
+  b200::scratch_cache().trim();
+  return had;
+}
+extern "C" size_t gdfx_scratch_cached_bytes() { return b200::scratch_cache().cached_bytes(); }
+extern "C" void gdfx_set_scratch_limit(size_t bytes) { b200::scratch_cache().set_limit(bytes); }
 
 extern "C" int gdfx_profile_enable(int on) {
   b200::Profiler& p = b200::prof();

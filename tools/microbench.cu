@@ -76,6 +76,55 @@ __global__ void match64_kernel(int iters, unsigned mask, unsigned* sink) {
   if (acc == 0x1234567) sink[0] = acc;
 }
 
+
+__global__ void gmem_red32_kernel(unsigned* tab, size_t mask, int iters) {
+  uint32_t s = blockIdx.x * 7919u + threadIdx.x * 104729u + 1u;
+  for (int i = 0; i < iters; ++i) {
+    size_t a = (((size_t)lcg(s) << 16) ^ lcg(s)) & mask;
+    atomicAdd(&tab[a], 1u);
+  }
+}
+__global__ void gmem_atom32_kernel(unsigned* tab, size_t mask, int iters, unsigned* sink) {  // returning atomic, 4 in flight
+  uint32_t s = blockIdx.x * 7919u + threadIdx.x * 104729u + 1u;
+  unsigned acc = 0;
+  for (int i = 0; i < iters; i += 4) {
+    size_t a0 = (((size_t)lcg(s) << 16) ^ lcg(s)) & mask, a1 = (((size_t)lcg(s) << 16) ^ lcg(s)) & mask;
+    size_t a2 = (((size_t)lcg(s) << 16) ^ lcg(s)) & mask, a3 = (((size_t)lcg(s) << 16) ^ lcg(s)) & mask;
+    unsigned r0 = atomicAdd(&tab[a0], 1u), r1 = atomicAdd(&tab[a1], 1u), r2 = atomicAdd(&tab[a2], 1u), r3 = atomicAdd(&tab[a3], 1u);
+    acc += r0 + r1 + r2 + r3;
+  }
+  if (acc == 0x1234567) sink[0] = acc;
+}
+// the "spill stream" pattern: every CTA appends 16-byte records to one of `streams` private regions, position
+// from a shared-memory cursor, no global atomics
+__global__ void append_kernel(uint4* region, unsigned streams, unsigned cap, int iters) {
+  extern __shared__ unsigned cur[];
+  for (unsigned i = threadIdx.x; i < streams; i += blockDim.x) cur[i] = 0;
+  __syncthreads();
+  uint32_t s = blockIdx.x * 7919u + threadIdx.x * 104729u + 1u;
+  for (int i = 0; i < iters; ++i) {
+    const unsigned p = lcg(s) % streams;
+    const unsigned pos = atomicAdd(&cur[p], 1u);
+    if (pos < cap) region[((size_t)p * gridDim.x + blockIdx.x) * cap + pos] = make_uint4(s, p, pos, i);
+  }
+}
+__global__ void gmem_read32_kernel(const ulonglong4* tab, size_t mask, int iters, unsigned* sink) {  // 32-byte buckets
+  uint32_t s = blockIdx.x * 7919u + threadIdx.x * 104729u + 1u;
+  unsigned long long acc = 0;
+  for (int i = 0; i < iters; i += 4) {
+    size_t a[4];
+    unsigned long long x[4], y[4], z[4], w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = (((size_t)lcg(s) << 16) ^ lcg(s)) & mask;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x[j]), "=l"(y[j]), "=l"(z[j]), "=l"(w[j]) : "l"(tab + a[j]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc += x[j] ^ y[j] ^ z[j] ^ w[j];
+  }
+  if (acc == 0x1234567) sink[0] = (unsigned)acc;
+}
+
 template <typename F>
 float time_ms(F f) {
   cudaEvent_t a, b;
@@ -114,6 +163,26 @@ int main() {
     ms = time_ms([&] { gmem_read16_kernel<<<blocks, threads>>>((const uint4*)tab, bytes / 16 - 1, iters / 4, (unsigned*)sink); });
     printf("gmem ld.128 random         in %5zu MB: %8.3f ms  %7.1f Gld/s  (%.0f GB/s of 32B sectors)\n", mb, ms, ops / 4 / ms * 1e-6, ops / 4 / ms * 1e-6 * 32);
     CK(cudaFree(tab));
+  }
+  for (size_t mb : {16ull, 64ull, 256ull}) {
+    size_t bytes = mb << 20;
+    unsigned* tab; CK(cudaMalloc(&tab, bytes)); CK(cudaMemset(tab, 0, bytes));
+    float ms = time_ms([&] { gmem_red32_kernel<<<blocks, threads>>>(tab, bytes / 4 - 1, iters / 4); });
+    printf("gmem red.add u32 random in %5zu MB: %8.3f ms  %7.1f Gop/s\n", mb, ms, ops / 4 / ms * 1e-6);
+    ms = time_ms([&] { gmem_atom32_kernel<<<blocks, threads>>>(tab, bytes / 4 - 1, iters / 4, (unsigned*)sink); });
+    printf("gmem atom.add u32 (returning, 4 in flight) random in %5zu MB: %8.3f ms  %7.1f Gop/s\n", mb, ms, ops / 4 / ms * 1e-6);
+    ms = time_ms([&] { gmem_read32_kernel<<<blocks, threads>>>((const ulonglong4*)tab, bytes / 32 - 1, iters / 4, (unsigned*)sink); });
+    printf("gmem ld.v4.u64 (32 B bucket) random in %5zu MB: %8.3f ms  %7.1f Gld/s\n", mb, ms, ops / 4 / ms * 1e-6);
+    CK(cudaFree(tab));
+  }
+  for (unsigned streams : {148u, 296u, 592u}) {
+    const unsigned cap = 16384, ablocks = sms, athreads = 1024;
+    const int aiters = (int)((size_t)cap * streams / athreads * 3 / 4);
+    uint4* region; CK(cudaMalloc(&region, (size_t)streams * ablocks * cap * 16));
+    float ms = time_ms([&] { append_kernel<<<ablocks, athreads, streams * 4>>>(region, streams, cap, aiters); });
+    const double recs = (double)ablocks * athreads * aiters;
+    printf("append 16 B records to %u streams/CTA (%d CTAs x 1024 thr): %8.3f ms  %7.1f Grec/s  %7.1f GB/s\n", streams, ablocks, ms, recs / ms * 1e-6, recs * 16 / ms * 1e-6);
+    CK(cudaFree(region));
   }
   {
     unsigned long long* one; CK(cudaMalloc(&one, 8)); CK(cudaMemset(one, 0, 8));
