@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--only", default="", help="comma list of join,groupby,filter (debug only)")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N>1: rows cross NVLink inside the partition kernel (peer memory) or via NCCL all_to_all")
+    ap.add_argument("--lab", action="store_true", help="load the -DB200_LAB build (libgdf_b200/lib_lab, make LAB=1): "
+                    "environment-variable knobs and timing ablations; never a bench value")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -62,9 +64,12 @@ def parse_args():
 # library loading: ours through the package, the reference through the same cdef
 # ------------------------------------------------------------------------------------------------
 class Api(object):
-    def __init__(self, impl):
+    def __init__(self, impl, lab=False):
         self.impl = impl
         if impl == "b200":
+            if lab:
+                import libgdf_b200
+                libgdf_b200.LIB_DIR = os.path.join(ROOT, "libgdf_b200", "lib_lab")
             from libgdf_b200.librmm_cffi import librmm, librmm_config
             librmm_config.use_pool_allocator = True
             librmm.finalize()
@@ -732,7 +737,7 @@ def main():
                       if args.scale == 1.0 else "scale %g" % args.scale)
 
     try:
-        api = Api(args.impl)
+        api = Api(args.impl, args.lab)
     except Exception as exc:  # reference library not built
         emit({"impl": args.impl, "unavailable": str(exc)})
         return 0

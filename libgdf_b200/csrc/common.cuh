@@ -99,6 +99,15 @@ struct KernelTimer {
 };
 #define B200_TIMED(name) ::b200::KernelTimer b200_kernel_timer__(name)
 
+// Lab knobs: A/B switches of kernel variants for tools/lab_*.py.  The shipped library has ONE behaviour: unless
+// it is built with -DB200_LAB (make LAB=1 -> lib_lab/), a knob is its compile-time default and no environment
+// variable is ever read.
+#ifdef B200_LAB
+int lab_knob(const char* name, int dflt);  // atoi(getenv(name)) or dflt
+#else
+inline int lab_knob(const char*, int dflt) { return dflt; }
+#endif
+
 // Small pinned host mailbox for "count" read-backs (one per host thread).
 void* pinned_mailbox();  // >= 256 bytes, cudaHostAlloc'd
 

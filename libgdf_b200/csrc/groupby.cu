@@ -19,9 +19,9 @@
 //     which cannot fail.  A key lives in exactly one level (slots are never freed, so a key that was
 //     placed is always found again within the probe bound), so the two result sets are disjoint;
 //   * values are folded with native L2 atomics (red.add / atom.min / atom.max), never CAS loops for
-//     integers; the single-key fast path keeps {key, accumulator} in one 16-byte slot so a row
-//     costs one 32-byte L2 sector, and pre-aggregates equal keys inside a warp with match.any so a
-//     Zipf-hot key costs one atomic per warp instead of one per row;
+//     integers; the single-key fast path (groupby_fast.cuh) puts a per-CTA shared-memory cache in front of
+//     the table so a Zipf-hot key costs a shared-memory atomic, and keeps the table's keys in 32-byte
+//     buckets so a cold key costs one L2 sector read and one red;
 //   * extraction compacts only the small table, with one cursor atomic per warp.
 #include <cstdlib>
 #include <limits>
@@ -205,17 +205,15 @@ extract_generic_kernel(TableView keys, KeyOut ko, const int32_t* __restrict__ sl
 // The all-ones key pattern doubles as the EMPTY marker; a real key with that value is folded into
 // a dedicated side slot (index `slots`).
 // ------------------------------------------------------------------------------------------
-struct alignas(16) FastSlot {
-  unsigned long long key;
-  int64_t acc;
-};
 constexpr unsigned long long kEmptyKey = ~0ull;
 
-__global__ void init_fast_kernel(FastSlot* tab, unsigned long long* cnt, size_t slots_plus_side, int64_t identity) {
+// keys[i] = EMPTY, acc[i] = identity, cnt[i] = 0 for the slots + the side slot
+__global__ void init_fast_kernel(unsigned long long* keys, int64_t* acc, unsigned long long* cnt, size_t slots_plus_side,
+                                 int64_t identity) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots_plus_side; i += stride) {
-    tab[i].key = kEmptyKey;
-    tab[i].acc = identity;
+    keys[i] = kEmptyKey;
+    acc[i] = identity;
     if (cnt) cnt[i] = 0;
   }
 }
@@ -235,29 +233,27 @@ static __device__ __forceinline__ void smem_add64(unsigned long long* acc, int64
 
 template <typename KT, typename IT, typename OT>
 __global__ void __launch_bounds__(kThreads)
-extract_fast_kernel(const FastSlot* __restrict__ tab, const unsigned long long* __restrict__ cnt, size_t slots,
-                    const int* __restrict__ side_used, int op, KT* __restrict__ out_keys, void* out_agg, int out_dtype,
-                    unsigned long long* cursor) {
+extract_fast_kernel(const unsigned long long* __restrict__ keys, const int64_t* __restrict__ acc,
+                    const unsigned long long* __restrict__ cnt, size_t slots, const int* __restrict__ side_used, int op,
+                    KT* __restrict__ out_keys, void* out_agg, int out_dtype, unsigned long long* cursor) {
   const size_t total = slots + 1;  // + side slot
   const size_t stride = (size_t)gridDim.x * kThreads;
   const size_t rounds = (total + stride - 1) / stride;
   for (size_t it = 0; it < rounds; ++it) {
     const size_t s = it * stride + (size_t)blockIdx.x * kThreads + threadIdx.x;
     bool have = false;
-    FastSlot sl{kEmptyKey, 0};
+    unsigned long long key = kEmptyKey;
     if (s < slots) {
-      sl = tab[s];
-      have = sl.key != kEmptyKey;
+      key = keys[s];
+      have = key != kEmptyKey;
     } else if (s == slots && *side_used) {
-      sl = tab[s];
-      sl.key = kEmptyKey;
-      have = true;
+      have = true;  // the side slot holds the real key that equals the EMPTY pattern
     }
     const size_t at = claim_output(have, cursor);
     if (have) {
-      out_keys[at] = (KT)sl.key;
-      if (op == OP_AVG) store_avg<IT>(out_agg, out_dtype, at, (IT)sl.acc, cnt[s]);
-      else store_acc<OT, int64_t>(out_agg, at, sl.acc);
+      out_keys[at] = (KT)key;
+      if (op == OP_AVG) store_avg<IT>(out_agg, out_dtype, at, (IT)acc[s], cnt[s]);
+      else store_acc<OT, int64_t>(out_agg, at, acc[s]);
     }
   }
 }
@@ -363,43 +359,41 @@ gdf_error groupby_fast(const KT* key_col, size_t n, const void* values, int op, 
   if (op == OP_MIN) identity = (int64_t)std::numeric_limits<VT>::max();
   if (op == OP_MAX) identity = (int64_t)std::numeric_limits<VT>::lowest();
   unsigned slots = pow2_at_least(2 * n);
-  static const unsigned level1 = getenv("B200_GB_SLOTS_LOG2") ? 1u << atoi(getenv("B200_GB_SLOTS_LOG2")) : kLevel1Slots;  // lab knob
+  if (slots < kBucketKeys) slots = kBucketKeys;
+  const unsigned level1 = (unsigned)lab_knob("B200_GB_SLOTS_LOG2", 0) ? 1u << lab_knob("B200_GB_SLOTS_LOG2", 0) : kLevel1Slots;
   const bool bounded = slots > level1;
   if (bounded) slots = level1;
-  Scratch tab, cnt;
-  B200_CUDA_TRY(tab.alloc(((size_t)slots + 1) * sizeof(FastSlot)));
+  Scratch keys, acc, cnt;
+  B200_CUDA_TRY(keys.alloc(((size_t)slots + kBucketKeys) * sizeof(unsigned long long)));
+  B200_CUDA_TRY(acc.alloc(((size_t)slots + 1) * sizeof(int64_t)));
   if (op == OP_AVG) B200_CUDA_TRY(cnt.alloc(((size_t)slots + 1) * sizeof(unsigned long long)));
   {
     B200_TIMED("groupby_init_table");
-    init_fast_kernel<<<grid_for((size_t)slots + 1), kThreads>>>(tab.as<FastSlot>(), cnt.as<unsigned long long>(),
-                                                               (size_t)slots + 1, identity);
+    init_fast_kernel<<<grid_for((size_t)slots + 1), kThreads>>>(keys.as<unsigned long long>(), acc.as<int64_t>(),
+                                                               cnt.as<unsigned long long>(), (size_t)slots + 1, identity);
   }
   B200_CHECK_LAST();
   const int fold_op = (op == OP_MIN) ? OP_MIN : (op == OP_MAX ? OP_MAX : OP_SUM);
   const bool count_rows = op == OP_COUNT, with_cnt = op == OP_AVG;
-  void (*kern)(const KT*, const VT*, size_t, FastSlot*, unsigned long long*, unsigned, unsigned, unsigned, int*,
-               unsigned long long*) = nullptr;
-  static const bool lean = getenv("B200_GROUPBY_LEAN") ? atoi(getenv("B200_GROUPBY_LEAN")) != 0 : false;  // lab knob
-  if (count_rows) kern = lean ? build_fast_kernel_v4<KT, VT, OP_SUM, true, false, true> : build_fast_kernel_v4<KT, VT, OP_SUM, true, false, false>;
-  else if (with_cnt) kern = lean ? build_fast_kernel_v4<KT, VT, OP_SUM, false, true, true> : build_fast_kernel_v4<KT, VT, OP_SUM, false, true, false>;
-  else if (fold_op == OP_MIN) kern = build_fast_kernel_v4<KT, VT, OP_MIN, false, false, false>;
-  else if (fold_op == OP_MAX) kern = build_fast_kernel_v4<KT, VT, OP_MAX, false, false, false>;
-  else kern = lean ? build_fast_kernel_v4<KT, VT, OP_SUM, false, false, true> : build_fast_kernel_v4<KT, VT, OP_SUM, false, false, false>;
+  void (*kern)(const KT*, const VT*, size_t, GlobalTable, int*, unsigned long long*, unsigned) = nullptr;
+  if (count_rows) kern = build_fast_kernel_v5<KT, VT, OP_SUM, true, false>;
+  else if (with_cnt) kern = build_fast_kernel_v5<KT, VT, OP_SUM, false, true>;
+  else if (fold_op == OP_MIN) kern = build_fast_kernel_v5<KT, VT, OP_MIN, false, false>;
+  else if (fold_op == OP_MAX) kern = build_fast_kernel_v5<KT, VT, OP_MAX, false, false>;
+  else kern = build_fast_kernel_v5<KT, VT, OP_SUM, false, false>;
   const int smem = (int)(sizeof(FastCache4) + (with_cnt ? kCacheSlots4 * sizeof(unsigned) : 0));
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   size_t want = (n + kGrabRows4 - 1) / kGrabRows4;                 // one warp-grab each
   want = (want + kFastThreads4 / 32 - 1) / (kFastThreads4 / 32);    // CTAs needed
   const size_t resident = (size_t)sm_count();                      // one 1024-thread CTA per SM
   const int blocks = (int)(want < resident ? (want ? want : 1) : resident);
+  // bounded table: a key that finds no room within kProbeLimitL1 slots reports overflow (generic path reruns it)
+  GlobalTable tab{keys.as<unsigned long long>(), acc.as<int64_t>(), cnt.as<unsigned long long>(), slots - 1,
+                  bounded ? kProbeLimitL1 / kBucketKeys : slots / kBucketKeys};
   {
     B200_TIMED("groupby_build_fast");
-    kern<<<blocks, kFastThreads4, smem>>>(key_col, static_cast<const VT*>(values), n, tab.as<FastSlot>(),
-                                          cnt.as<unsigned long long>(), slots - 1, slots,
-                                          (bounded ? kProbeLimitL1 : slots)
-#ifdef B200_LAB_GROUPBY
-                                              | (getenv("B200_LAB_GB") ? (unsigned)atoi(getenv("B200_LAB_GB")) << 28 : 0u)
-#endif
-                                          , flags, cursor + 3);
+    kern<<<blocks, kFastThreads4, smem>>>(key_col, static_cast<const VT*>(values), n, tab, flags, cursor + 3,
+                                          (unsigned)lab_knob("B200_LAB_GB", 0));
   }
   B200_CHECK_LAST();
   if (bounded) {
@@ -413,7 +407,8 @@ gdf_error groupby_fast(const KT* key_col, size_t n, const void* values, int op, 
   {
     B200_TIMED("groupby_extract");
     extract_fast_kernel<KT, VT, OT><<<grid_for((size_t)slots + 1), kThreads>>>(
-        tab.as<FastSlot>(), cnt.as<unsigned long long>(), slots, flags, op, out_keys, out_agg, out_dtype, cursor);
+        keys.as<unsigned long long>(), acc.as<int64_t>(), cnt.as<unsigned long long>(), slots, flags, op, out_keys, out_agg,
+        out_dtype, cursor);
   }
   B200_CHECK_LAST();
   unsigned long long groups = 0;

@@ -1,26 +1,35 @@
-// Single-key group-by build kernel (v4).  Included by groupby.cu inside its anonymous namespace,
-// after FastSlot / fold() / smem_add64() are defined.
+// Single-key group-by build kernel (v5).  Included by groupby.cu inside its anonymous namespace,
+// after fold() / smem_add64() / kEmptyKey are defined.
 //
-// History (profiles/r01a_ncu_full_summary.md): v3 ran C4 at 1.58 TB/s with the issue slots 70 % busy -
-// about 230 SASS instructions per row (MurmurHash3 per row, a 4-probe cache loop, a non-inlined
-// global fold, dynamically indexed register arrays that ptxas spilled to local memory).  The kernel was
-// instruction-bound, not memory-bound.  v4 is the same algorithm with the instruction count cut:
-//   * the table position comes from a 3-multiply mixer (the hash is internal: nothing observable
-//     depends on it, unlike gdf_hash / gdf_hash_partition which keep MurmurHash3);
-//   * the per-CTA cache is 2-way set associative and a set is ONE 128-bit shared-memory load;
-//   * rows are read with 128-bit loads (two 8-byte rows per load), four rows per lane per step,
-//     everything fully unrolled so that all per-row state stays in registers;
-//   * the op (sum / min / max), "count rows" and "keep a row count for AVG" are template parameters.
-// One CTA of 1024 threads per SM owns an 8192-slot cache (128 KB of shared memory); rows whose key is
-// not cached fold straight into the L2-resident global table with red.global.  The input stream is
-// staged one step ahead with cp.async (64 KB).  Variants that were measured and lost (miss queue, lock-step
-// inline-PTX cache phase, deferred misses with 768 threads): profiles/r01b_experiments.md.
+// One CTA of 1024 threads per SM owns an 8192-slot, 2-way set-associative cache of {key, accumulator}
+// in shared memory (a set's two keys are ONE 128-bit shared-memory load).  Under Zipf skew the cache absorbs
+// ~65 % of the rows with shared-memory atomics; rows whose key is not cached fold into ONE L2-resident global
+// table with red.global.  The input stream is staged one step ahead with cp.async (L2 evict_first).
+//
+// History.  v3 -> v4 (profiles/r01a, r01b): the instruction count per row was cut from 233 to 105 and the kernel
+// went from 10.1 to 7.1 ms at C4.  What bounded v4 (profiles/r02_microbench.txt, r02_notes.md): a row that missed
+// the cache walked the global table slot by slot ({key,acc} in 16 bytes, linear probing at load 0.24), one row
+// after the other.  14 % of those walks need a second DEPENDENT L2 round trip, and with ~11 missing lanes per
+// warp-row nearly every one of the four rows of a step paid it: +2.2 us per 128-row step, although the same
+// B200 retires 1.9e11 spread-address red.add.u64 per second when nothing depends on a load.
+// v5 removes the dependent walks:
+//   * the global table is split into a key array and an accumulator array and is BUCKETISED: the home of a key
+//     is an aligned group of BK keys (32 bytes = one L2 sector for BK = 4) fetched with one vector load; at load
+//     0.24 a key lives outside its home bucket with probability 0.3 %, so the common miss is exactly one L2 round
+//     trip + one fire-and-forget red, for all rows of the step at once;
+//   * the step is reordered: cache sets of all four rows are examined first, the bucket loads of the misses are
+//     issued (two rows at a time: 1024 threads leave 64 registers each, and four 32-byte buckets spilled), the
+//     shared-memory atomics of the hits run while those loads are in flight, then the misses are resolved;
+//   * everything else (claim of an empty slot, bucket overflow, the side slot for a key equal to the EMPTY
+//     pattern) is one out-of-line slow path.
 #pragma once
 
 constexpr int kFastThreads4 = 1024;
 constexpr unsigned kCacheSets4 = 4096;                 // x 2 ways
 constexpr unsigned kCacheSlots4 = 2 * kCacheSets4;
 constexpr unsigned kGrabRows4 = 32 * 4 * 32;           // rows per warp per work grab (4096)
+constexpr unsigned kBucketKeys = 4;                    // keys per global bucket: 4 x 8 B = one 32-byte sector
+constexpr int kMissBatch = 2;                          // rows whose bucket loads are in flight together (register budget: 64)
 
 struct FastCache4 {
   unsigned long long key[kCacheSlots4];   // way pairs are adjacent: one LDS.128 per set
@@ -38,7 +47,7 @@ static __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gm
                : "memory");
 }
 
-// Internal position hash.  h's top bits pick the cache set, its low bits the global slot.
+// Internal position hash.  h's top bits pick the cache set, its low bits the global bucket.
 static __device__ __forceinline__ uint32_t mix_key(unsigned long long k) {
   uint32_t x = (uint32_t)k * 0x9E3779B1u ^ (uint32_t)(k >> 32) * 0x85EBCA77u;
   x ^= x >> 15;
@@ -54,34 +63,56 @@ static __device__ __forceinline__ void cache_fold(unsigned long long* acc, int64
   else atomicMax(reinterpret_cast<long long*>(acc), (long long)v);
 }
 
-// Fold (v, c) for `key` into the global table starting at slot s whose key word `k0` is already loaded.
+// The L2-resident global table: keys and accumulators in separate arrays, `slots` a power of two (a multiple of
+// kBucketKeys), plus one side slot at index `slots` for a real key equal to the EMPTY pattern.
+struct GlobalTable {
+  unsigned long long* keys;
+  int64_t* acc;
+  unsigned long long* cnt;   // per-slot row counts, AVG only
+  unsigned mask;             // slots - 1
+  unsigned probe_buckets;    // give up (overflow flag) after this many buckets
+};
+
+struct Bucket4 {
+  unsigned long long k[kBucketKeys];
+};
+static __device__ __forceinline__ Bucket4 ld_bucket(const unsigned long long* p) {  // 32-byte aligned, L2 only
+  Bucket4 b;
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.k[0]), "=l"(b.k[1]), "=l"(b.k[2]), "=l"(b.k[3]) : "l"(p));
+  return b;
+}
+
+// Everything that is not "the key sits in its home bucket": claim an EMPTY slot (first occurrence of a key),
+// walk on when the bucket is full of other keys.  Restarts at the home bucket.  Out of line on purpose: it keeps
+// the registers of the hot loop free (v3 inlined a loop like this one and spilled).
 template <int FOLD, bool WITH_CNT>
-static __device__ __forceinline__ bool global_fold4(FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt,
-                                                    unsigned mask, unsigned probe_limit, unsigned s,
-                                                    unsigned long long k0, unsigned long long key, int64_t v,
-                                                    unsigned long long c) {
-  for (unsigned probe = 0; probe < probe_limit; ++probe) {
-    if (k0 == kEmptyKey) {
-      const unsigned long long prev = atomicCAS(&tab[s].key, kEmptyKey, key);
-      k0 = (prev == kEmptyKey) ? key : prev;
+static __device__ __noinline__ bool global_fold_slow(GlobalTable t, unsigned bucket, unsigned long long key, int64_t v,
+                                                     unsigned long long c) {
+  for (unsigned probe = 0; probe < t.probe_buckets; ++probe) {
+#pragma unroll 1
+    for (unsigned j = 0; j < kBucketKeys; ++j) {
+      const unsigned s = bucket + j;
+      unsigned long long k0 = *reinterpret_cast<volatile unsigned long long*>(&t.keys[s]);
+      if (k0 == kEmptyKey) {
+        const unsigned long long prev = atomicCAS(&t.keys[s], kEmptyKey, key);
+        k0 = (prev == kEmptyKey) ? key : prev;
+      }
+      if (k0 == key) {
+        fold(&t.acc[s], v, FOLD);
+        if (WITH_CNT) atomicAdd(&t.cnt[s], c);
+        return true;
+      }
     }
-    if (k0 == key) {
-      fold(&tab[s].acc, v, FOLD);
-      if (WITH_CNT) atomicAdd(&cnt[s], c);
-      return true;
-    }
-    s = (s + 1) & mask;
-    k0 = tab[s].key;
+    bucket = (bucket + kBucketKeys) & t.mask;
   }
   return false;
 }
 
-template <typename KT, typename IT, int FOLD, bool COUNT_ROWS, bool WITH_CNT, bool LEAN>
+template <typename KT, typename IT, int FOLD, bool COUNT_ROWS, bool WITH_CNT>
 __global__ void __launch_bounds__(kFastThreads4, 1)
-build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ values, size_t n,
-                     FastSlot* __restrict__ tab, unsigned long long* __restrict__ cnt, unsigned mask, unsigned slots,
-                     unsigned probe_limit, int* __restrict__ flags /*[0]=side slot used, [1]=overflow*/,
-                     unsigned long long* __restrict__ work_counter) {
+build_fast_kernel_v5(const KT* __restrict__ key_col, const IT* __restrict__ values, size_t n, GlobalTable tab,
+                     int* __restrict__ flags /*[0]=side slot used, [1]=overflow*/,
+                     unsigned long long* __restrict__ work_counter, unsigned lab) {
   using UK = typename std::conditional<sizeof(KT) == 8, unsigned long long, unsigned>::type;
   constexpr bool VEC = sizeof(KT) == 8 && sizeof(IT) == 8;  // two rows per 128-bit load
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -113,70 +144,22 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
     staged_step = st;
   };
 
-  // LEAN (additive folds): 32-bit shared addresses computed once (no generic->shared conversion per access)
-  // and the carry of the 64-bit shared-memory add examined at the END of the step, so the ATOMS round trip
-  // of a row is not waited for before the next row starts.
-  const uint32_t s_key = (uint32_t)__cvta_generic_to_shared(&cache.key[0]);
-  const uint32_t s_acc = (uint32_t)__cvta_generic_to_shared(&cache.acc[0]);
-  uint32_t lean_old[4], lean_slot[4];
-  bool lean_hit[4];
-  auto cache_try_lean = [&](int u, unsigned long long k, int64_t v, uint32_t h) -> bool {
-    const unsigned set2 = (h >> 20) * 2u;
-    ulonglong2 kk;
-    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(kk.x), "=l"(kk.y) : "r"(s_key + set2 * 8u));
-    lean_hit[u] = false;
-    int way = -1;
-    if (kk.x == k) way = 0;
-    else if (kk.y == k) way = 1;
-    if (way >= 0) {
-      lean_slot[u] = set2 + (unsigned)way;
-      asm volatile("atom.shared.add.u32 %0, [%1], %2;"
-                   : "=r"(lean_old[u])
-                   : "r"(s_acc + lean_slot[u] * 8u), "r"((uint32_t)(unsigned long long)v));
-      lean_hit[u] = true;
-      if (WITH_CNT) atomicAdd(&ccnt[lean_slot[u]], 1u);
-      return true;
+  // Cache set of row (k, h): returns the slot index (set*2 + way) holding k, or -1.  A set with a free way is
+  // claimed on the spot (cold start only; slots are never freed, so a key that was placed is always found again).
+  auto cache_slot = [&](unsigned long long k, uint32_t h) -> int {
+    const unsigned set2 = (h >> 20) * 2u;  // top 12 bits
+    const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(&cache.key[set2]);
+    if (kk.x == k) return (int)set2;
+    if (kk.y == k) return (int)set2 + 1;
+    if (kk.x == kEmptyKey) {
+      const unsigned long long prev = atomicCAS(&cache.key[set2], kEmptyKey, k);
+      if (prev == kEmptyKey || prev == k) return (int)set2;
     }
-    if (kk.x == kEmptyKey || kk.y == kEmptyKey) {  // cold start only: claim a free way
-      if (kk.x == kEmptyKey) {
-        const unsigned long long prev = atomicCAS(&cache.key[set2], kEmptyKey, k);
-        if (prev == kEmptyKey || prev == k) way = 0;
-      }
-      if (way < 0) {
-        const unsigned long long prev = atomicCAS(&cache.key[set2 + 1], kEmptyKey, k);
-        if (prev == kEmptyKey || prev == k) way = 1;
-      }
-      if (way >= 0) {
-        cache_fold<FOLD>(&cache.acc[set2 + way], v);
-        if (WITH_CNT) atomicAdd(&ccnt[set2 + way], 1u);
-        return true;
-      }
+    if (kk.x == kEmptyKey || kk.y == kEmptyKey) {
+      const unsigned long long prev = atomicCAS(&cache.key[set2 + 1], kEmptyKey, k);
+      if (prev == kEmptyKey || prev == k) return (int)set2 + 1;
     }
-    return false;
-  };
-
-  // one row: cache first, then the global table.  gk = key word of the row's first global slot,
-  // loaded by the caller for all rows of a step before any of them is resolved.
-  auto cache_try = [&](unsigned long long k, int64_t v, uint32_t h) -> bool {
-    const unsigned set = h >> 20;  // top 12 bits
-    const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(&cache.key[2 * set]);
-    int way = -1;
-    if (kk.x == k) way = 0;
-    else if (kk.y == k) way = 1;
-    else if (kk.x == kEmptyKey || kk.y == kEmptyKey) {  // cold start only: claim a free way
-      if (kk.x == kEmptyKey) {
-        const unsigned long long prev = atomicCAS(&cache.key[2 * set], kEmptyKey, k);
-        if (prev == kEmptyKey || prev == k) way = 0;
-      }
-      if (way < 0) {
-        const unsigned long long prev = atomicCAS(&cache.key[2 * set + 1], kEmptyKey, k);
-        if (prev == kEmptyKey || prev == k) way = 1;
-      }
-    }
-    if (way < 0) return false;
-    cache_fold<FOLD>(&cache.acc[2 * set + way], v);
-    if (WITH_CNT) atomicAdd(&ccnt[2 * set + way], 1u);
-    return true;
+    return -1;
   };
 
   while (true) {
@@ -219,44 +202,64 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
           v[u] = (live[u] && !COUNT_ROWS) ? (int64_t)values[r] : 1;
         }
       }
-      uint32_t h[4];
-      bool miss[4];
+      // (1) cache sets of all four rows.  loc[u] >= 0: cache slot holding the key; loc[u] == kDead: nothing left
+      // to do for this row; otherwise ~loc[u] is the first slot of the key's home bucket in the global table.
+      constexpr int kDead = INT_MIN;
+      int loc[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        h[u] = mix_key(k[u]);
-        miss[u] = live[u];
-        if (LEAN) lean_hit[u] = false;
-        if (live[u] && k[u] != kEmptyKey) miss[u] = LEAN ? !cache_try_lean(u, k[u], v[u], h[u]) : !cache_try(k[u], v[u], h[u]);
-      }
-#ifdef B200_LAB_GROUPBY   // timing experiments of profiles/r01b_experiments.md (wrong results): -DB200_LAB_GROUPBY
-      if (probe_limit & 0x40000000u) continue;   // B200_LAB_GB=4: drop the global path entirely
-#endif
-      // rows that missed the cache: first global slots fetched together, then resolved
-      unsigned long long gk[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) gk[u] = (miss[u] && k[u] != kEmptyKey) ? tab[h[u] & mask].key : kEmptyKey;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (!miss[u]) continue;
+        loc[u] = kDead;
+        if (!live[u]) continue;
         if (k[u] == kEmptyKey) {  // a real key equal to the EMPTY pattern lives in the side slot
-          fold(&tab[slots].acc, v[u], FOLD);
-          if (WITH_CNT) atomicAdd(&cnt[slots], 1ull);
+          fold(&tab.acc[tab.mask + 1], v[u], FOLD);
+          if (WITH_CNT) atomicAdd(&tab.cnt[tab.mask + 1], 1ull);
           flags[0] = 1;
-#ifdef B200_LAB_GROUPBY
-        } else if (probe_limit & 0x20000000u) {    // B200_LAB_GB=2: load the slot key, skip the fold
-          if (gk[u] == 12345ull) flags[1] = 1;
-#endif
-        } else if (!global_fold4<FOLD, WITH_CNT>(tab, cnt, mask, probe_limit & 0x0fffffffu, h[u] & mask, gk[u], k[u], v[u], 1ull)) {
-          flags[1] = 1;
+          continue;
         }
+        const uint32_t h = mix_key(k[u]);
+        const int s = cache_slot(k[u], h);
+        loc[u] = s >= 0 ? s : ~(int)((h & tab.mask) & ~(kBucketKeys - 1));
       }
-      if (LEAN) {
+#ifdef B200_LAB   // timing ablation of profiles/r02_notes.md (wrong results by design): cache phase only
+      if (lab & 4u) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (!lean_hit[u]) continue;
-          const uint32_t lo = (uint32_t)(unsigned long long)v[u];
-          const uint32_t up = (uint32_t)((unsigned long long)v[u] >> 32) + (uint32_t)((uint32_t)(lean_old[u] + lo) < lean_old[u]);
-          if (up) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(s_acc + lean_slot[u] * 8u + 4u), "r"(up) : "memory");
+        for (int u = 0; u < 4; ++u)
+          if (loc[u] >= 0) cache_fold<FOLD>(&cache.acc[loc[u]], v[u]);
+        continue;
+      }
+#endif
+      // (2) misses are resolved kMissBatch rows at a time: home buckets fetched together, then examined - the key
+      // sits in its home bucket (one red) or the slow path takes over.  (3) The shared-memory folds of ALL hits are
+      // issued right after the first batch of loads, so they run while those loads are in flight.
+#pragma unroll
+      for (int u0 = 0; u0 < 4; u0 += kMissBatch) {
+        Bucket4 bk[kMissBatch];
+#pragma unroll
+        for (int q = 0; q < kMissBatch; ++q)
+          if (loc[u0 + q] < 0 && loc[u0 + q] != kDead) bk[q] = ld_bucket(tab.keys + (unsigned)~loc[u0 + q]);
+        if (u0 == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (loc[u] < 0) continue;
+            cache_fold<FOLD>(&cache.acc[loc[u]], v[u]);
+            if (WITH_CNT) atomicAdd(&ccnt[loc[u]], 1u);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kMissBatch; ++q) {
+          const int u = u0 + q;
+          if (loc[u] >= 0 || loc[u] == kDead) continue;
+          const unsigned b = (unsigned)~loc[u];
+          int j = -1;
+#pragma unroll
+          for (int w = (int)kBucketKeys - 1; w >= 0; --w)
+            if (bk[q].k[w] == k[u]) j = w;
+          if (j >= 0) {
+            fold(&tab.acc[b + j], v[u], FOLD);
+            if (WITH_CNT) atomicAdd(&tab.cnt[b + j], 1ull);
+          } else if (!global_fold_slow<FOLD, WITH_CNT>(tab, b, k[u], v[u], 1ull)) {
+            flags[1] = 1;
+          }
         }
       }
     }
@@ -265,9 +268,8 @@ build_fast_kernel_v4(const KT* __restrict__ key_col, const IT* __restrict__ valu
   for (unsigned i = threadIdx.x; i < kCacheSlots4; i += kFastThreads4) {
     const unsigned long long ck = cache.key[i];
     if (ck == kEmptyKey) continue;
-    const unsigned s = mix_key(ck) & mask;
-    if (!global_fold4<FOLD, WITH_CNT>(tab, cnt, mask, probe_limit, s, tab[s].key, ck, (int64_t)cache.acc[i],
-                                      WITH_CNT ? (unsigned long long)ccnt[i] : 0ull))
+    const unsigned b = (mix_key(ck) & tab.mask) & ~(kBucketKeys - 1);
+    if (!global_fold_slow<FOLD, WITH_CNT>(tab, b, ck, (int64_t)cache.acc[i], WITH_CNT ? (unsigned long long)ccnt[i] : 0ull))
       flags[1] = 1;
   }
 }

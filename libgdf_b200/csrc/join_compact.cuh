@@ -1,0 +1,602 @@
+// Compact (32-bit key) kernels of the radix-partitioned join.  Included by join_part.cu inside its anonymous
+// namespace, after KeyBits / slot_hash / PartGeom.
+//
+// When every valid BUILD key fits in 32 bits (int32 key columns always; int64 key columns whose high words are all
+// zero - detected for free by the histogram pass: ids, C3) a probe key with a non-zero high word cannot match, so
+//   * the partitioned pairs are {key32, tag32} = 8 bytes instead of 12 (scatter writes and probe reads shrink by a
+//     third),
+//   * a table slot is the 8-byte word {key32 | row32 << 32}: insert = ONE 64-bit CAS (no second store), and four
+//     slots fill one 32-byte L2 sector.  Tables are BUCKETISED: a key's home is an aligned group of four slots
+//     fetched with one 256-bit load; at load <= 0.5 the key (or the EMPTY slot that proves its absence) is in
+//     the home bucket for ~98 % of the rows, so a probe is exactly one L2 round trip.  EMPTY = all ones: the row
+//     word of a real entry is a row id < 2^31.
+//
+// Probe kernel (profiles/r02_notes.md; what round 1 established: a CTA barrier + one returning cursor atomic per
+// 1-2 K-row tile caps a kernel at ~2 TB/s of its stream however the tile is fed):
+//   * WARP-INDEPENDENT: no __syncthreads after the prologue.  Every warp owns a 4-stage ring of 256-pair (2 KB)
+//     tiles filled by cp.async.bulk (TMA) with an mbarrier per stage; lane 0 is the producer, the warp releases a
+//     stage with __syncwarp once all lanes hold their pairs in registers.  Tiles are dealt round-robin over all
+//     warps of the grid, so the warps in flight work inside a window of ~600 K consecutive pairs - one or two
+//     partitions, whose tables stay L2-resident;
+//   * 8 bucket loads in flight per lane; stragglers (home bucket full of other keys, ~2 %) are resolved in warp-wide
+//     rounds;
+//   * ranks inside the warp come from ballots; output space comes from PER-WARP CHUNKS of the output arrays
+//     (2048 pairs, one cursor atomic per chunk, requested one tile before it is needed, so no atomic is on a warp's
+//     critical path).  A chunk is filled densely, a tile that crosses a chunk boundary is split.  What stays
+//     unused at the end (at most two partial chunks per warp) is recorded as HOLES, and a fix-up pass moves the
+//     tail of the output into them (<= 4736 x 2048 pairs, ~20 us) so that the caller sees one dense column;
+//   * LEFT joins with unique build keys emit exactly one pair per probe row: the output position is the pair's
+//     position, no allocation at all.  Duplicate build keys: exact count pass, then one cursor atomic per warp tile.
+#pragma once
+
+constexpr int kC32Threads = 512;
+constexpr int kC32Warps = kC32Threads / 32;
+constexpr int kC32Rows = 8;                      // pairs per lane per tile
+constexpr int kC32Tile = 32 * kC32Rows;          // 256 pairs = 2 KB
+constexpr int kC32Stages = 4;
+constexpr unsigned kC32Chunk = 2048;             // output pairs per chunk
+constexpr unsigned long long kEmpty32 = ~0ull;
+
+struct Tables32 {
+  unsigned long long* slots;           // {key32 | row32 << 32}
+  const unsigned long long* offset;    // [nparts] first slot of partition p
+  const unsigned* mask;                // [nparts] slots_p - 1, slots_p a power of two >= 4
+};
+
+struct Pairs32 {
+  const uint2* pairs;  // .x = key, .y = tag (row id; ~row id for rows that can never match: NULL key / wide key)
+  size_t n;
+};
+
+struct Bucket32 {
+  unsigned long long w[4];
+};
+static __device__ __forceinline__ Bucket32 ld_bucket32(const unsigned long long* p) {  // 32-byte aligned; L2 only (tables
+  Bucket32 b;                                                                         // are written by the build kernel)
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.w[0]), "=l"(b.w[1]), "=l"(b.w[2]), "=l"(b.w[3]) : "l"(p));
+  return b;
+}
+static __device__ __forceinline__ Bucket32 ld_bucket32_hint(const unsigned long long* p, uint64_t policy) {
+  Bucket32 b;
+  asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+               : "=l"(b.w[0]), "=l"(b.w[1]), "=l"(b.w[2]), "=l"(b.w[3])
+               : "l"(p), "l"(policy));
+  return b;
+}
+static __device__ __forceinline__ bool slot_empty(unsigned long long w) { return (uint32_t)(w >> 32) == 0xffffffffu; }
+
+// ---- build: one 64-bit CAS per row into the first EMPTY slot of its bucket ----
+// One CTA = one contiguous tile of pairs, tiles dispatched in index order (the pairs are partition-contiguous, so
+// the CTAs in flight insert into one or two partitions' tables, which stay L2-resident).  Every thread keeps four
+// inserts in flight and resolves them in rounds: (a) load the bucket of every row that needs one, (b) pick the
+// first EMPTY slot of the local copy, (c) issue all CAS, (d) examine - a failed CAS returns the occupant, which
+// updates the local copy (no reload) and is checked for "same key" = duplicate build key.  Two equal keys walk the
+// same slot sequence and slots never empty, so the later one always sees the earlier one: flags[0] is exact.
+constexpr int kB32Threads = 256;
+constexpr int kB32U = 4;
+constexpr int kB32Tile = kB32Threads * kB32U;
+
+__global__ void __launch_bounds__(kB32Threads)
+build32_kernel(Pairs32 b, PartGeom g, Tables32 t, int* __restrict__ flags /*[0]=dup*/) {
+  const size_t tile_lo = (size_t)blockIdx.x * kB32Tile;
+  unsigned long long mine[kB32U], prev[kB32U];
+  unsigned long long* tab[kB32U];
+  unsigned at[kB32U], mask[kB32U];
+  int cand[kB32U];
+  Bucket32 bk[kB32U];
+  unsigned pend = 0, need = 0;
+#pragma unroll
+  for (int u = 0; u < kB32U; ++u) {
+    const size_t i = tile_lo + (size_t)u * kB32Threads + threadIdx.x;
+    mine[u] = 0;
+    tab[u] = t.slots;
+    at[u] = 0;
+    mask[u] = 3;
+    if (i < b.n) {
+      const uint2 pr = b.pairs[i];
+      mine[u] = ((unsigned long long)pr.y << 32) | pr.x;
+      const uint32_t h = KeyBits<uint32_t>::hash(pr.x);
+      const unsigned p = g.pid(h);
+      tab[u] = t.slots + t.offset[p];
+      mask[u] = t.mask[p];
+      at[u] = (slot_hash(h) & mask[u]) & ~3u;
+      pend |= 1u << u;
+    }
+  }
+  need = pend;
+  bool dup = false;
+  while (pend) {
+#pragma unroll
+    for (int u = 0; u < kB32U; ++u)
+      if ((need >> u) & 1u) bk[u] = ld_bucket32(tab[u] + at[u]);
+    need = 0;
+#pragma unroll
+    for (int u = 0; u < kB32U; ++u) {
+      cand[u] = -1;
+      if (!((pend >> u) & 1u)) continue;
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {
+        if (slot_empty(bk[u].w[j])) cand[u] = j;
+        else if ((uint32_t)bk[u].w[j] == (uint32_t)mine[u]) dup = true;
+      }
+      if (cand[u] < 0) {  // bucket full of other keys: next bucket, loaded in the next round
+        at[u] = (at[u] + 4u) & mask[u];
+        need |= 1u << u;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kB32U; ++u)
+      if (((pend >> u) & 1u) && cand[u] >= 0) prev[u] = atomicCAS(tab[u] + at[u] + cand[u], kEmpty32, mine[u]);
+#pragma unroll
+    for (int u = 0; u < kB32U; ++u) {
+      if (!((pend >> u) & 1u) || cand[u] < 0) continue;
+      if (prev[u] == kEmpty32) {
+        pend &= ~(1u << u);
+      } else {  // somebody else took the slot: remember the occupant, try the next EMPTY slot of the local copy
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j == cand[u]) bk[u].w[j] = prev[u];
+      }
+    }
+  }
+  if (dup) flags[0] = 1;
+}
+
+// ---- probe ----
+enum Probe32Mode { P32_COUNT = 0, P32_CURSOR = 1, P32_CHUNK = 2, P32_POSITIONAL = 3 };
+
+struct Probe32Out {
+  int32_t* probe;
+  int32_t* build;
+  unsigned long long* cursor;        // COUNT: total matches; CURSOR: output cursor; CHUNK: chunk cursor (multiples of kC32Chunk)
+  unsigned long long* hole_start;    // CHUNK: [2 * warps of the grid]
+  unsigned* hole_len;
+};
+
+struct Probe32Smem {
+  uint64_t bar[kC32Warps][kC32Stages];
+  unsigned long long part_off[kMaxParts];
+  unsigned part_mask[kMaxParts];
+};
+constexpr size_t probe32_smem_bytes() {
+  return (size_t)kC32Warps * kC32Stages * kC32Tile * sizeof(uint2) + sizeof(Probe32Smem) + 128;
+}
+
+static __device__ __forceinline__ void st_i32_stream(int32_t* p, int32_t v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
+}
+static __device__ __forceinline__ void bulk_load_policy(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                        uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          tma::smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(tma::smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+template <bool LEFT_LIKE, bool UNIQUE, int MODE>
+__global__ void __launch_bounds__(kC32Threads, 1)
+probe32_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, unsigned lab) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint2* const ring_all = reinterpret_cast<uint2*>(smem_raw);
+  Probe32Smem& sm = *reinterpret_cast<Probe32Smem*>(smem_raw + (size_t)kC32Warps * kC32Stages * kC32Tile * sizeof(uint2));
+  const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const size_t tiles = (pr.n + kC32Tile - 1) / kC32Tile;
+  const size_t gw = (size_t)blockIdx.x * kC32Warps + warp;       // this warp's index in the grid
+  const size_t W = (size_t)gridDim.x * kC32Warps;                // warps of the grid: tile of iteration i = i * W + gw
+  uint2* const ring = ring_all + (size_t)warp * kC32Stages * kC32Tile;
+  uint64_t* const bar = sm.bar[warp];
+  uint64_t pol_stream, pol_table;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_table));
+
+  for (unsigned p = tid; p < g.nparts; p += kC32Threads) {
+    sm.part_off[p] = t.offset[p];
+    sm.part_mask[p] = t.mask[p];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kC32Stages; ++s) tma::mbar_init(&bar[s], 1);
+    tma::fence_barrier_init();
+  }
+  __syncthreads();  // the only CTA-wide barrier: partition geometry + barriers are set up
+
+  auto issue = [&](size_t it) {  // lane 0: start the copy of this warp's tile of iteration `it` (full tiles only)
+    const size_t tl = it * W + gw;
+    if (tl < tiles && (tl + 1) * kC32Tile <= pr.n) {
+      const int s = (int)(it % kC32Stages);
+      tma::mbar_expect_tx(&bar[s], kC32Tile * (uint32_t)sizeof(uint2));
+      bulk_load_policy(ring + (size_t)s * kC32Tile, pr.pairs + tl * kC32Tile, kC32Tile * (uint32_t)sizeof(uint2), &bar[s],
+                       pol_stream);
+    }
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kC32Stages; ++s) issue((size_t)s);
+  }
+
+  // per-warp output chunk state (MODE == P32_CHUNK); identical in all lanes except `next_base` (lane 0 holds it)
+  unsigned long long chunk_base = 0, next_base = 0;
+  unsigned chunk_used = kC32Chunk;  // "no chunk yet"
+  bool have_next = false;
+  unsigned long long counted = 0;   // P32_COUNT: matches seen by this lane
+
+  for (size_t it = 0;; ++it) {
+    const size_t tl = it * W + gw;
+    if (tl >= tiles) break;
+    const size_t row0 = tl * kC32Tile;
+    const bool full = row0 + kC32Tile <= pr.n;
+    const int s = (int)(it % kC32Stages);
+    if (MODE == P32_CHUNK && !have_next && chunk_used + kC32Tile > kC32Chunk) {
+      // the tile may overflow the current chunk: ask for the next one now, use it (if at all) after the look-ups
+      if (lane == 0) next_base = atomicAdd(out.cursor, (unsigned long long)kC32Chunk);
+      have_next = true;
+    }
+    uint32_t key[kC32Rows];
+    int32_t tag[kC32Rows];
+    if (full) {
+      tma::mbar_wait(&bar[s], (unsigned)(it / kC32Stages) & 1u);
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        const uint2 v = ring[(size_t)s * kC32Tile + i * 32 + lane];
+        key[i] = v.x;
+        tag[i] = (int32_t)v.y;
+      }
+      __syncwarp();  // every lane holds its pairs: the stage can be refilled
+      if (lane == 0) {
+        tma::fence_proxy_async();
+        issue(it + kC32Stages);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        const size_t j = row0 + i * 32 + lane;
+        uint2 v = make_uint2(0u, 0x80000000u);  // past the end: tag INT_MIN = "no row"
+        if (j < pr.n) v = pr.pairs[j];
+        key[i] = v.x;
+        tag[i] = (int32_t)v.y;
+      }
+    }
+    // ---- look-ups: every row's home bucket in flight, then examined ----
+    int32_t first[kC32Rows];
+    unsigned cnt[kC32Rows];
+    unsigned where[kC32Rows];   // partition << 24 | bucket's first slot   (slots per partition <= 2^24)
+    Bucket32 bk[kC32Rows];
+    unsigned pend = 0;
+#pragma unroll
+    for (int i = 0; i < kC32Rows; ++i) {
+      first[i] = -1;
+      const bool have = full || (tag[i] != (int32_t)0x80000000);
+      cnt[i] = (LEFT_LIKE && have) ? 1u : 0u;
+      const uint32_t h = KeyBits<uint32_t>::hash(key[i]);
+      const unsigned p = g.pid(h);
+      where[i] = (p << 24) | ((slot_hash(h) & sm.part_mask[p]) & ~3u);
+      bool look = have && tag[i] >= 0;  // negative tag: the row can never match (NULL key / wide key)
+#ifdef B200_LAB
+      if ((lab & 1u) && look) { look = false; cnt[i] = 1; first[i] = 0; }   // ablation: no table look-up
+#endif
+      if (look) {
+        pend |= 1u << i;
+        bk[i] = ld_bucket32_hint(t.slots + sm.part_off[p] + (where[i] & 0xffffffu), pol_table);
+      }
+    }
+    unsigned multi = 0;  // !UNIQUE: rows with more than one match (re-walked when written)
+    while (true) {
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        if (!((pend >> i) & 1u)) continue;
+        bool stop = false;
+        unsigned c = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned long long w = bk[i].w[j];
+          if (slot_empty(w)) stop = true;           // the chain of this key ends in this bucket
+          else if ((uint32_t)w == key[i]) {
+            if (first[i] < 0) first[i] = (int32_t)(uint32_t)(w >> 32);
+            ++c;
+          }
+        }
+        if (c) {
+          if (UNIQUE) stop = true;
+          if (LEFT_LIKE && !(multi >> i & 1u) && cnt[i] == 1 && first[i] >= 0 && !((multi >> (8 + i)) & 1u)) {
+            cnt[i] = 0;                    // the provisional (row,-1) pair is replaced by real matches
+            multi |= 1u << (8 + i);        // bit 8+i: "matched at least once"
+          }
+          cnt[i] += c;
+        }
+        if (stop) pend &= ~(1u << i);
+      }
+      if (!__any_sync(0xffffffffu, pend != 0)) break;
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        if (!((pend >> i) & 1u)) continue;
+        const unsigned p = where[i] >> 24;
+        const unsigned at = ((where[i] & 0xffffffu) + 4u) & sm.part_mask[p];
+        where[i] = (p << 24) | at;
+        bk[i] = ld_bucket32_hint(t.slots + sm.part_off[p] + at, pol_table);
+      }
+    }
+    if (MODE == P32_COUNT) {
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) counted += cnt[i];
+      continue;
+    }
+    if (MODE == P32_POSITIONAL) {  // LEFT_LIKE && UNIQUE: exactly one pair per row, at the row's own position
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        const size_t j = row0 + i * 32 + lane;
+        if (j < pr.n) {
+          st_i32_stream(out.probe + j, tag[i] >= 0 ? tag[i] : ~tag[i], pol_stream);
+          st_i32_stream(out.build + j, first[i], pol_stream);
+        }
+      }
+      continue;
+    }
+    // ---- ranks inside the warp (row-major: row i of all lanes, then row i + 1) ----
+    unsigned rank[kC32Rows], total = 0;
+#pragma unroll
+    for (int i = 0; i < kC32Rows; ++i) {
+      if (UNIQUE) {  // counts are 0 / 1
+        const unsigned bal = __ballot_sync(0xffffffffu, cnt[i] != 0);
+        rank[i] = total + __popc(bal & lanemask_lt());
+        total += __popc(bal);
+      } else {
+        unsigned inc = cnt[i];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= (unsigned)d) inc += o;
+        }
+        rank[i] = total + inc - cnt[i];
+        total += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+#ifdef B200_LAB
+    if (lab & 2u) continue;   // ablation: no output stores
+#endif
+    if (MODE == P32_CURSOR) {
+      unsigned long long base = 0;
+      if (lane == 0 && total) base = atomicAdd(out.cursor, (unsigned long long)total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        size_t pos = (size_t)base + rank[i];
+        const int32_t prow = tag[i] >= 0 ? tag[i] : ~tag[i];
+        if (cnt[i] == 1) {
+          out.probe[pos] = prow;
+          out.build[pos] = first[i];
+        } else if (cnt[i] > 1) {  // duplicate build keys: walk the chain again
+          const uint32_t h = KeyBits<uint32_t>::hash(key[i]);
+          const unsigned p = g.pid(h);
+          const unsigned long long* tb = t.slots + sm.part_off[p];
+          unsigned at = (slot_hash(h) & sm.part_mask[p]) & ~3u;
+          bool stop = false;
+          while (!stop) {
+            const Bucket32 b = ld_bucket32_hint(tb + at, pol_table);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (slot_empty(b.w[j])) stop = true;
+              else if ((uint32_t)b.w[j] == key[i]) {
+                out.probe[pos] = prow;
+                out.build[pos] = (int32_t)(uint32_t)(b.w[j] >> 32);
+                ++pos;
+              }
+            }
+            at = (at + 4u) & sm.part_mask[p];
+          }
+        }
+      }
+      continue;
+    }
+    // ---- MODE == P32_CHUNK (UNIQUE, INNER): dense fill of per-warp chunks ----
+    unsigned in_old = total;                       // pairs of this tile that still fit the current chunk
+    unsigned long long old_at = chunk_base + chunk_used, new_base = 0;
+    if (chunk_used + total > kC32Chunk) {
+      in_old = kC32Chunk - chunk_used;
+      new_base = __shfl_sync(0xffffffffu, next_base, 0);   // requested at the top of an earlier or this iteration
+      chunk_base = new_base;
+      chunk_used = total - in_old;
+      have_next = false;
+    } else {
+      chunk_used += total;
+    }
+#pragma unroll
+    for (int i = 0; i < kC32Rows; ++i) {
+      if (cnt[i] == 0) continue;
+      const size_t pos = rank[i] < in_old ? (size_t)(old_at + rank[i]) : (size_t)(new_base + (rank[i] - in_old));
+      st_i32_stream(out.probe + pos, tag[i], pol_stream);
+      st_i32_stream(out.build + pos, first[i], pol_stream);
+    }
+  }
+  if (MODE == P32_COUNT) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, d);
+    if (lane == 0 && counted) atomicAdd(out.cursor, counted);
+  }
+  if (MODE == P32_CHUNK && lane == 0) {  // what this warp reserved and did not fill
+    out.hole_start[2 * gw] = chunk_base + chunk_used;
+    out.hole_len[2 * gw] = kC32Chunk - chunk_used;
+    out.hole_start[2 * gw + 1] = next_base;
+    out.hole_len[2 * gw + 1] = have_next ? kC32Chunk : 0u;
+  }
+}
+
+// ---- fix-up of the chunked output: move the tail into the holes ----
+// plan kernel (one CTA): sorts the holes by position, computes found = allocated - sum(hole lengths), and two
+// segment lists with exclusive prefix sums: RECEIVERS = hole positions below `found`, DONORS = filled positions at or
+// above `found`.  Both lists describe the same number of pairs (moved).  move kernel: pair m of the donors goes to
+// position m of the receivers.
+constexpr int kFixThreads = 1024;
+constexpr int kFixCap = 8192;   // >= 2 * warps of the probe grid (148 SMs x 16 warps x 2 = 4736)
+
+struct FixPlan {          // device memory, filled by fixup_plan_kernel
+  unsigned long long found, moved;
+  unsigned n_recv, n_donor;
+  unsigned long long recv_start[kFixCap + 1], donor_start[kFixCap + 1];
+  unsigned recv_pre[kFixCap + 2], donor_pre[kFixCap + 2];   // exclusive prefix sums of the segment lengths (+ total)
+};
+
+// exclusive scan of v[0..kFixCap) in place (shared memory), returns the total; all kFixThreads threads call it
+static __device__ unsigned fix_scan(unsigned* v, unsigned* warp_sums) {
+  constexpr int PER = kFixCap / kFixThreads;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  unsigned loc[PER], sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    loc[j] = v[tid * PER + j];
+    sum += loc[j];
+  }
+  unsigned inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= (unsigned)d) inc += o;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  unsigned off = 0, tot = 0;
+  for (int w = 0; w < kFixThreads / 32; ++w) {
+    const unsigned ws = warp_sums[w];
+    if ((unsigned)w < warp) off += ws;
+    tot += ws;
+  }
+  unsigned run = off + inc - sum;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    v[tid * PER + j] = run;
+    run += loc[j];
+  }
+  __syncthreads();
+  return tot;
+}
+
+__global__ void __launch_bounds__(kFixThreads)
+fixup_plan_kernel(const unsigned long long* __restrict__ hole_start, const unsigned* __restrict__ hole_len, unsigned n_holes,
+                  const unsigned long long* __restrict__ cursor, FixPlan* __restrict__ plan) {
+  extern __shared__ __align__(16) unsigned char fix_smem[];
+  unsigned long long* hs = reinterpret_cast<unsigned long long*>(fix_smem);          // [kFixCap] start << 24 | idx? no: start
+  unsigned* hl = reinterpret_cast<unsigned*>(hs + kFixCap);                          // [kFixCap] length
+  unsigned* len_a = hl + kFixCap;                                                    // [kFixCap] receiver lengths
+  unsigned* len_b = len_a + kFixCap;                                                 // [kFixCap] donor lengths
+  __shared__ unsigned warp_sums[kFixThreads / 32];
+  const unsigned tid = threadIdx.x;
+  const unsigned long long allocated = *cursor;
+  // sort key: start (40 bits are plenty) << 24 | length (<= 2048); empty entries sort last
+  for (unsigned i = tid; i < kFixCap; i += kFixThreads) {
+    unsigned long long k = ~0ull;
+    if (i < n_holes && hole_len[i] != 0) k = (hole_start[i] << 24) | hole_len[i];
+    hs[i] = k;
+  }
+  __syncthreads();
+  for (unsigned size = 2; size <= kFixCap; size <<= 1) {       // bitonic sort, ascending
+    for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+      for (unsigned i = tid; i < kFixCap / 2; i += kFixThreads) {
+        const unsigned lo = 2 * i - (i & (stride - 1));
+        const unsigned hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = hs[lo], b = hs[hi];
+        if ((a > b) == up) {
+          hs[lo] = b;
+          hs[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (unsigned i = tid; i < kFixCap; i += kFixThreads) {
+    const unsigned long long k = hs[i];
+    hl[i] = k == ~0ull ? 0u : (unsigned)(k & 0xffffffu);
+  }
+  __syncthreads();
+  for (unsigned i = tid; i < kFixCap; i += kFixThreads) len_a[i] = hl[i];
+  __syncthreads();
+  const unsigned long long holes_total = fix_scan(len_a, warp_sums);
+  const unsigned long long found = allocated - holes_total;
+  // receivers: hole i clipped to [0, found).  donors: the filled gap BEFORE hole i clipped to [found, allocated),
+  // entry kFixCap - 1 doubles as "the gap after the last hole" (there are at most 4736 real holes)
+  for (unsigned i = tid; i < kFixCap; i += kFixThreads) {
+    const unsigned long long k = hs[i];
+    unsigned ra = 0, db = 0;
+    if (k != ~0ull) {
+      const unsigned long long st = k >> 24, en = st + hl[i];
+      if (st < found) ra = (unsigned)((en < found ? en : found) - st);
+      unsigned long long prev_end = 0;
+      if (i > 0) prev_end = (hs[i - 1] >> 24) + hl[i - 1];
+      const unsigned long long gs = prev_end > found ? prev_end : found;
+      if (st > gs) db = (unsigned)(st - gs);
+    } else if (i == kFixCap - 1) {
+      unsigned long long last_end = 0;
+      // the last real hole is the last non-empty entry: scan back (only this one thread does it)
+      for (int j = (int)kFixCap - 2; j >= 0; --j)
+        if (hs[j] != ~0ull) {
+          last_end = (hs[j] >> 24) + hl[j];
+          break;
+        }
+      const unsigned long long gs = last_end > found ? last_end : found;
+      if (allocated > gs) db = (unsigned)(allocated - gs);
+    }
+    len_a[i] = ra;
+    len_b[i] = db;
+  }
+  __syncthreads();
+  // segment start positions (before the scans overwrite the lengths)
+  for (unsigned i = tid; i < kFixCap; i += kFixThreads) {
+    const unsigned long long k = hs[i];
+    unsigned long long rs = 0, ds = 0;
+    if (k != ~0ull) {
+      rs = k >> 24;
+      unsigned long long prev_end = 0;
+      if (i > 0) prev_end = (hs[i - 1] >> 24) + hl[i - 1];
+      ds = prev_end > found ? prev_end : found;
+    } else if (i == kFixCap - 1) {
+      unsigned long long last_end = 0;
+      for (int j = (int)kFixCap - 2; j >= 0; --j)
+        if (hs[j] != ~0ull) {
+          last_end = (hs[j] >> 24) + hl[j];
+          break;
+        }
+      ds = last_end > found ? last_end : found;
+    }
+    plan->recv_start[i] = rs;
+    plan->donor_start[i] = ds;
+  }
+  const unsigned moved_a = fix_scan(len_a, warp_sums);
+  const unsigned moved_b = fix_scan(len_b, warp_sums);
+  for (unsigned i = tid; i < kFixCap; i += kFixThreads) {
+    plan->recv_pre[i] = len_a[i];
+    plan->donor_pre[i] = len_b[i];
+  }
+  if (tid == 0) {
+    plan->recv_pre[kFixCap] = moved_a;
+    plan->donor_pre[kFixCap] = moved_b;
+    plan->found = found;
+    plan->moved = moved_a < moved_b ? moved_a : moved_b;  // equal by construction
+    plan->n_recv = kFixCap;
+    plan->n_donor = kFixCap;
+  }
+}
+
+// last index i in [0, n) with pre[i] <= m  (pre is an exclusive prefix sum, non-decreasing; zero-length segments
+// share a prefix with their successor, so "last" lands on the segment that really contains m)
+static __device__ __forceinline__ unsigned seg_of(const unsigned* __restrict__ pre, unsigned n, unsigned m) {
+  unsigned lo = 0, hi = n;  // invariant: pre[lo] <= m, pre[hi] > m  (pre[n] = total > m)
+  while (hi - lo > 1) {
+    const unsigned mid = (lo + hi) >> 1;
+    if (pre[mid] <= m) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+fixup_move_kernel(const FixPlan* __restrict__ plan, int32_t* __restrict__ a, int32_t* __restrict__ b) {
+  const unsigned moved = (unsigned)plan->moved;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < moved; m += stride) {
+    const unsigned r = seg_of(plan->recv_pre, kFixCap, m), d = seg_of(plan->donor_pre, kFixCap, m);
+    const size_t to = (size_t)(plan->recv_start[r] + (m - plan->recv_pre[r]));
+    const size_t from = (size_t)(plan->donor_start[d] + (m - plan->donor_pre[d]));
+    a[to] = a[from];
+    b[to] = b[from];
+  }
+}

@@ -8,6 +8,7 @@
 #include <vector>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include <nvtx3/nvToolsExt.h>
 
@@ -59,6 +60,13 @@ rmmError_t output_alloc(void** p, size_t bytes) {
   }
   return r;
 }
+
+#ifdef B200_LAB
+int lab_knob(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+#endif
 
 void* pinned_mailbox() {
   static thread_local void* box = nullptr;
