@@ -70,7 +70,7 @@ static __device__ __forceinline__ bool slot_empty(unsigned long long w) { return
 // the CTAs in flight insert into one or two partitions' tables, which stay L2-resident).  Every thread keeps four
 // inserts in flight and resolves them in rounds: (a) load the bucket of every row that needs one, (b) pick the
 // first EMPTY slot of the local copy, (c) issue all CAS, (d) examine - a failed CAS returns the occupant, which
-// updates the local copy (no reload) and is checked for "same key" = duplicate build key.  Two equal keys walk the
+// is checked for "same key" = duplicate build key and marks the slot as taken (no reload).  Two equal keys walk the
 // same slot sequence and slots never empty, so the later one always sees the earlier one: flags[0] is exact.
 constexpr int kB32Threads = 256;
 constexpr int kB32U = 4;
@@ -82,6 +82,7 @@ build32_kernel(Pairs32 b, PartGeom g, Tables32 t, int* __restrict__ flags /*[0]=
   unsigned long long mine[kB32U], prev[kB32U];
   unsigned long long* tab[kB32U];
   unsigned at[kB32U], mask[kB32U];
+  unsigned taken[kB32U];  // slots of the current bucket that a failed CAS showed to be occupied (bit j)
   int cand[kB32U];
   Bucket32 bk[kB32U];
   unsigned pend = 0, need = 0;
@@ -92,6 +93,7 @@ build32_kernel(Pairs32 b, PartGeom g, Tables32 t, int* __restrict__ flags /*[0]=
     tab[u] = t.slots;
     at[u] = 0;
     mask[u] = 3;
+    taken[u] = 0;
     if (i < b.n) {
       const uint2 pr = b.pairs[i];
       mine[u] = ((unsigned long long)pr.y << 32) | pr.x;
@@ -108,17 +110,26 @@ build32_kernel(Pairs32 b, PartGeom g, Tables32 t, int* __restrict__ flags /*[0]=
   while (pend) {
 #pragma unroll
     for (int u = 0; u < kB32U; ++u)
-      if ((need >> u) & 1u) bk[u] = ld_bucket32(tab[u] + at[u]);
+      if ((need >> u) & 1u) {
+        bk[u] = ld_bucket32(tab[u] + at[u]);
+        taken[u] = 0;
+      }
+    // keys already in the bucket are compared once, right after the load
+#pragma unroll
+    for (int u = 0; u < kB32U; ++u) {
+      if (!((need >> u) & 1u)) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!slot_empty(bk[u].w[j]) && (uint32_t)bk[u].w[j] == (uint32_t)mine[u]) dup = true;
+    }
     need = 0;
 #pragma unroll
     for (int u = 0; u < kB32U; ++u) {
       cand[u] = -1;
       if (!((pend >> u) & 1u)) continue;
 #pragma unroll
-      for (int j = 3; j >= 0; --j) {
-        if (slot_empty(bk[u].w[j])) cand[u] = j;
-        else if ((uint32_t)bk[u].w[j] == (uint32_t)mine[u]) dup = true;
-      }
+      for (int j = 3; j >= 0; --j)
+        if (slot_empty(bk[u].w[j]) && !((taken[u] >> j) & 1u)) cand[u] = j;
       if (cand[u] < 0) {  // bucket full of other keys: next bucket, loaded in the next round
         at[u] = (at[u] + 4u) & mask[u];
         need |= 1u << u;
@@ -132,10 +143,9 @@ build32_kernel(Pairs32 b, PartGeom g, Tables32 t, int* __restrict__ flags /*[0]=
       if (!((pend >> u) & 1u) || cand[u] < 0) continue;
       if (prev[u] == kEmpty32) {
         pend &= ~(1u << u);
-      } else {  // somebody else took the slot: remember the occupant, try the next EMPTY slot of the local copy
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j == cand[u]) bk[u].w[j] = prev[u];
+      } else {  // somebody else took the slot since the bucket was loaded: note it, compare, try the next EMPTY slot
+        taken[u] |= 1u << cand[u];
+        if ((uint32_t)prev[u] == (uint32_t)mine[u]) dup = true;
       }
     }
   }
@@ -177,9 +187,9 @@ static __device__ __forceinline__ void bulk_load_policy(void* smem_dst, const vo
 template <bool LEFT_LIKE, bool UNIQUE, int MODE>
 __global__ void __launch_bounds__(kC32Threads, 1)
 probe32_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, unsigned lab) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint2* const ring_all = reinterpret_cast<uint2*>(smem_raw);
-  Probe32Smem& sm = *reinterpret_cast<Probe32Smem*>(smem_raw + (size_t)kC32Warps * kC32Stages * kC32Tile * sizeof(uint2));
+  extern __shared__ __align__(128) unsigned char probe32_smem[];
+  uint2* const ring_all = reinterpret_cast<uint2*>(probe32_smem);
+  Probe32Smem& sm = *reinterpret_cast<Probe32Smem*>(probe32_smem + (size_t)kC32Warps * kC32Stages * kC32Tile * sizeof(uint2));
   const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   const size_t tiles = (pr.n + kC32Tile - 1) / kC32Tile;
   const size_t gw = (size_t)blockIdx.x * kC32Warps + warp;       // this warp's index in the grid
@@ -280,7 +290,7 @@ probe32_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, unsigned lab)
         bk[i] = ld_bucket32_hint(t.slots + sm.part_off[p] + (where[i] & 0xffffffu), pol_table);
       }
     }
-    unsigned multi = 0;  // !UNIQUE: rows with more than one match (re-walked when written)
+    unsigned matched = 0;  // bit i: row i has found at least one partner
     while (true) {
 #pragma unroll
       for (int i = 0; i < kC32Rows; ++i) {
@@ -297,12 +307,10 @@ probe32_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, unsigned lab)
           }
         }
         if (c) {
-          if (UNIQUE) stop = true;
-          if (LEFT_LIKE && !(multi >> i & 1u) && cnt[i] == 1 && first[i] >= 0 && !((multi >> (8 + i)) & 1u)) {
-            cnt[i] = 0;                    // the provisional (row,-1) pair is replaced by real matches
-            multi |= 1u << (8 + i);        // bit 8+i: "matched at least once"
-          }
+          if (LEFT_LIKE && !((matched >> i) & 1u)) cnt[i] = 0;  // real matches replace the provisional (row,-1) pair
+          matched |= 1u << i;
           cnt[i] += c;
+          if (UNIQUE) stop = true;
         }
         if (stop) pend &= ~(1u << i);
       }

@@ -98,15 +98,25 @@ struct PartGeom {
 // ---- pass 1: per-partition row counts.  Shared-memory 32-bit atomics are the cheapest primitive on
 // B200 for this (~2900 Gop/s measured, profiles/r01_microbench.txt; match.any-based ranking measured
 // 20x slower), so the CTA histogram is plain atomicAdd on shared counters. ----
-template <typename KT, bool KEEP_NULLS>
+// COMPACT (join_compact.cuh): rows whose 64-bit key has a non-zero high word cannot match a 32-bit build side and
+// are counted like NULL-key rows.  hi_or (if not null) receives the OR of the high words of all valid keys - the
+// build-side launch uses it to find out whether the compact path applies at all.
+template <typename KT, bool KEEP_NULLS, bool COMPACT>
 __global__ void __launch_bounds__(kThreads)
 part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
                  unsigned long long* __restrict__ totals, const uint32_t* __restrict__ k2,
-                 const gdf_valid_type* __restrict__ valid2) {
+                 const gdf_valid_type* __restrict__ valid2, unsigned* __restrict__ hi_or) {
   __shared__ unsigned hist[kMaxParts];
   for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads) hist[p] = 0;
   __syncthreads();
   const size_t stride = (size_t)gridDim.x * kThreads;
+  uint32_t hi_acc = 0;
+  auto wide = [&](KT k) -> bool {  // high word of an 8-byte key (always false for 4-byte keys)
+    if (sizeof(KT) != 8) return false;
+    const uint32_t hi = (uint32_t)((unsigned long long)k >> 32);
+    hi_acc |= hi;
+    return COMPACT && hi != 0;
+  };
   if (valid == nullptr && valid2 == nullptr && k2 == nullptr && aligned16(keys)) {  // no mask: 128-bit loads, 4 in flight per thread
     constexpr int VEC = 16 / (int)sizeof(KT), U = 4;
     const size_t nvec = n / VEC;
@@ -120,15 +130,22 @@ part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (v0 + (size_t)u * stride >= nvec) continue;
+        const size_t v = v0 + (size_t)u * stride;
+        if (v >= nvec) continue;
         const KT* e = reinterpret_cast<const KT*>(&raw[u]);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(e[j]))], 1u);
+        for (int j = 0; j < VEC; ++j) {
+          if (!wide(e[j])) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(e[j]))], 1u);
+          else if (KEEP_NULLS) atomicAdd(&hist[(unsigned)(v * VEC + j) & (g.nparts - 1)], 1u);
+        }
       }
     }
     if (blockIdx.x == 0 && threadIdx.x < VEC) {  // ragged tail
       const size_t r = nvec * VEC + threadIdx.x;
-      if (r < n) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(keys[r]))], 1u);
+      if (r < n) {
+        if (!wide(keys[r])) atomicAdd(&hist[g.pid(KeyBits<KT>::hash(keys[r]))], 1u);
+        else if (KEEP_NULLS) atomicAdd(&hist[(unsigned)r & (g.nparts - 1)], 1u);
+      }
     }
   } else {
     constexpr int U = 8;
@@ -143,7 +160,7 @@ part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__
       for (int u = 0; u < U; ++u) {
         const size_t r = r0 + (size_t)u * stride;
         if (r >= n) continue;
-        if (bit_valid(valid, r) && bit_valid(valid2, r)) {
+        if (bit_valid(valid, r) && bit_valid(valid2, r) && !wide(k[u])) {
           uint32_t h = KeyBits<KT>::hash(k[u]);
           if (k2) h = with_k2(h, k2[r]);
           atomicAdd(&hist[g.pid(h)], 1u);
@@ -156,6 +173,10 @@ part_hist_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__
   __syncthreads();
   for (unsigned p = threadIdx.x; p < g.nparts; p += kThreads)
     if (hist[p]) atomicAdd(&totals[p], (unsigned long long)hist[p]);
+  if (hi_or != nullptr && sizeof(KT) == 8) {
+    hi_acc = __reduce_or_sync(0xffffffffu, hi_acc);
+    if (lane_id() == 0 && hi_acc) atomicOr(hi_or, hi_acc);
+  }
 }
 
 // ---- pass 2: write-combining scatter of {key,row} pairs ----
@@ -309,6 +330,111 @@ part_scatter_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restric
     // histogram of this tile (hist[buf]) is cleared during the NEXT tile's phase (2)
   }
 }
+
+// ---- compact scatter: {key32, tag32} pairs in ONE 8-byte array (join_compact.cuh) ----
+// Same tile protocol as part_scatter_kernel; the staged tile is 32 KB of pairs + a partition byte per element, so
+// four 256-thread CTAs are resident per SM instead of three (128 KB of input in flight per SM instead of 96).  Rows with a NULL key or a
+// key that does not fit 32 bits are dropped (build side, INNER probe side) or kept with tag = ~row (LEFT / FULL).
+constexpr int kS32Threads = 256;
+constexpr int kS32Rows = 16;
+constexpr int kS32Tile = kS32Threads * kS32Rows;  // 4096
+
+struct Scatter32Smem {
+  uint2 pairs[kS32Tile];
+  unsigned char pid[kS32Tile];
+  unsigned hist[2][kMaxParts];
+  unsigned lstart[kMaxParts];
+  unsigned long long gbase[kMaxParts];
+};
+
+template <typename KT, bool KEEP_NULLS>
+__global__ void __launch_bounds__(kS32Threads, sizeof(KT) == 8 ? 3 : 4)
+part_scatter32_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
+                      unsigned long long* __restrict__ cursors, uint2* __restrict__ out_pairs,
+                      const int32_t* __restrict__ payload, int32_t id_base) {
+  extern __shared__ __align__(16) unsigned char scatter32_smem[];
+  Scatter32Smem& sm = *reinterpret_cast<Scatter32Smem*>(scatter32_smem);
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const size_t tiles = (n + kS32Tile - 1) / kS32Tile;
+  for (unsigned p = threadIdx.x; p < 2 * kMaxParts; p += kS32Threads) (&sm.hist[0][0])[p] = 0;
+  __syncthreads();
+  unsigned buf = 0;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1u) {
+    const size_t wbase = tile * kS32Tile + (size_t)warp * (32 * kS32Rows);
+    uint32_t k[kS32Rows];  // low key words; bit i of `wide` = row i's key does not fit 32 bits
+    unsigned wide = 0;
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      const size_t r = wbase + (size_t)i * 32 + lane;
+      const KT kk = r < n ? keys[r] : (KT)0;
+      k[i] = (uint32_t)kk;
+      if (sizeof(KT) == 8 && (uint32_t)((unsigned long long)kk >> 32) != 0) wide |= 1u << i;
+    }
+    unsigned rp[kS32Rows];  // rank << 16 | pid, 0xffff = dropped, bit 15 = row that can never match
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      const size_t r = wbase + (size_t)i * 32 + lane;
+      bool keep = r < n;
+      unsigned p = 0, nullbit = 0;
+      if (keep) {
+        if (!((wide >> i) & 1u) && bit_valid(valid, r)) p = g.pid(KeyBits<uint32_t>::hash(k[i]));
+        else if (KEEP_NULLS) { p = (unsigned)r & (g.nparts - 1); nullbit = 0x8000u; }
+        else keep = false;
+      }
+      rp[i] = keep ? ((atomicAdd(&sm.hist[buf][p], 1u) << 16) | p | nullbit) : 0xffffu;
+    }
+    __syncthreads();  // (1) tile histogram complete
+    {
+      const unsigned p = threadIdx.x;
+      if (p < g.nparts) {
+        const unsigned run = sm.hist[buf][p];
+        sm.gbase[p] = run ? atomicAdd(&cursors[p], (unsigned long long)run) : 0ull;
+      }
+      if (p < kMaxParts) sm.hist[buf ^ 1u][p] = 0;  // the other buffer, for the next tile
+    }
+    if (warp == kS32Threads / 32 - 1) {  // exclusive scan of the <= 256 partition counts (8 per lane)
+      unsigned c[kMaxParts / 32], tot = 0;
+#pragma unroll
+      for (int j = 0; j < (int)(kMaxParts / 32); ++j) {
+        const unsigned p = lane * (kMaxParts / 32) + j;
+        c[j] = p < g.nparts ? sm.hist[buf][p] : 0;
+        tot += c[j];
+      }
+      unsigned inc = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += o;
+      }
+      unsigned run = inc - tot;
+#pragma unroll
+      for (int j = 0; j < (int)(kMaxParts / 32); ++j) {
+        const unsigned p = lane * (kMaxParts / 32) + j;
+        if (p < g.nparts) sm.lstart[p] = run;
+        run += c[j];
+      }
+    }
+    __syncthreads();  // (2) lstart visible (the previous tile's copy-out finished before barrier (1))
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      if ((rp[i] & 0xffffu) == 0xffffu) continue;
+      const unsigned p = rp[i] & 0x7fffu;
+      const unsigned at = sm.lstart[p] + (rp[i] >> 16);
+      const size_t row = wbase + (size_t)i * 32 + lane;
+      const int32_t r = payload ? payload[row] : (int32_t)row + id_base;
+      sm.pairs[at] = make_uint2(k[i], (uint32_t)((rp[i] & 0x8000u) ? ~r : r));
+      sm.pid[at] = (unsigned char)p;
+    }
+    __syncthreads();  // (3) staged tile + gbase complete
+    const unsigned kept = sm.lstart[g.nparts - 1] + sm.hist[buf][g.nparts - 1];
+    for (unsigned j = threadIdx.x; j < kept; j += kS32Threads) {
+      const unsigned p = sm.pid[j];
+      out_pairs[sm.gbase[p] + (j - sm.lstart[p])] = sm.pairs[j];
+    }
+  }
+}
+
+#include "join_compact.cuh"
 
 // Where the pairs of one side live.  rows == nullptr means "not partitioned": key i belongs to row i
 // and `valid` (if any) still applies.
@@ -474,9 +600,6 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
         mask[i] = t.mask[p];
         start[i] = slot_hash(h) & mask[i];
         lookup[i] = true;
-#ifdef B200_LAB_PROBE   // timing ablations (wrong results): g.dest bit 8 = no table look-up, bit 9 = no output stores
-        if (g.dest & 0x100u) { lookup[i] = false; cnt[i] = 1; first[i] = 0; }
-#endif
       }
       if (LEFT_LIKE) cnt[i] = 1;  // at least (row,-1)
     }
@@ -510,9 +633,6 @@ part_probe_kernel(Pairs<KT> pr, PartGeom g, Tables t, int32_t* __restrict__ out_
   }
   if (threadIdx.x == 0) tile_out = tile_total ? atomicAdd(cursor, (unsigned long long)tile_total) : 0ull;
   if (!WRITE) return;
-#ifdef B200_LAB_PROBE
-  if (g.dest & 0x200u) return;
-#endif
   __syncthreads();
   size_t pos0 = (size_t)tile_out;
 #pragma unroll
@@ -725,9 +845,6 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
       first[i] = -1;
       cnt[i] = (LEFT_LIKE && have) ? 1u : 0u;
       lookup[i] = ok && key[i] != kEmptyKey;
-#ifdef B200_LAB_PROBE
-      if ((g.dest & 0x100u) && lookup[i]) { lookup[i] = false; cnt[i] = 1; first[i] = 0; }
-#endif
       const uint32_t h = KeyBits<KT>::hash(kraw);
       const unsigned p = g.pid(h);
       where[i] = (p << 24) | (slot_hash(h) & sm.part_mask[p]);
@@ -879,9 +996,6 @@ part_probe_stream_kernel(Pairs<KT> pr /* rows != nullptr */, PartGeom g, Tables 
       sm.tile_out[buf] = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
     }
     if (!WRITE) continue;  // count-only pass: the cursor is the result (tile_out is double-buffered)
-#ifdef B200_LAB_PROBE
-    if (g.dest & 0x200u) continue;
-#endif
     __syncthreads();
     size_t pos0 = (size_t)sm.tile_out[buf];
     for (unsigned w = 0; w < warp; ++w) pos0 += sm.warp_tot[buf][w];
@@ -964,21 +1078,48 @@ unsigned pow2_at_least(size_t x) {
   return p;
 }
 
-template <typename KT, bool KEEP_NULLS>
-gdf_error partition_hist(const gdf_column* col, PartGeom g, unsigned long long* d_totals /*device [nparts]*/,
-                         unsigned long long* h_totals, const gdf_column* col2 = nullptr) {
+template <typename KT, bool KEEP_NULLS, bool COMPACT = false>
+gdf_error partition_hist(const gdf_column* col, PartGeom g, unsigned long long* d_totals /*device [nparts + 1]*/,
+                         unsigned long long* h_totals, const gdf_column* col2 = nullptr, unsigned* h_hi_or = nullptr) {
   const KT* keys = static_cast<const KT*>(col->data);
   const size_t n = col->size;
-  B200_CUDA_TRY(cudaMemsetAsync(d_totals, 0, g.nparts * sizeof(unsigned long long), 0));
+  // d_totals[nparts] doubles as the "OR of the high key words" cell
+  B200_CUDA_TRY(cudaMemsetAsync(d_totals, 0, (g.nparts + 1) * sizeof(unsigned long long), 0));
   const int blocks = sm_count() * 4;
   {
     B200_TIMED("join_part_hist");
-    part_hist_kernel<KT, KEEP_NULLS><<<blocks, kThreads>>>(keys, col->valid, n, g, d_totals,
-                                                           col2 ? static_cast<const uint32_t*>(col2->data) : nullptr,
-                                                           col2 ? col2->valid : nullptr);
+    part_hist_kernel<KT, KEEP_NULLS, COMPACT><<<blocks, kThreads>>>(keys, col->valid, n, g, d_totals,
+                                                                    col2 ? static_cast<const uint32_t*>(col2->data) : nullptr,
+                                                                    col2 ? col2->valid : nullptr,
+                                                                    reinterpret_cast<unsigned*>(d_totals + g.nparts));
   }
   B200_CHECK_LAST();
-  B200_CUDA_TRY(cudaMemcpy(h_totals, d_totals, g.nparts * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long h_all[kMaxParts + 1];
+  B200_CUDA_TRY(cudaMemcpy(h_all, d_totals, (g.nparts + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (unsigned p = 0; p < g.nparts; ++p) h_totals[p] = h_all[p];
+  if (h_hi_or) *h_hi_or = (unsigned)h_all[g.nparts];
+  return GDF_SUCCESS;
+}
+
+template <typename KT, bool KEEP_NULLS>
+gdf_error partition_scatter32(const gdf_column* col, PartGeom g, const unsigned long long* h_cursors,
+                              unsigned long long* d_cursors, uint2* out_pairs, const int32_t* payload, int32_t id_base) {
+  const KT* keys = static_cast<const KT*>(col->data);
+  const size_t n = col->size;
+  B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  auto kern = part_scatter32_kernel<KT, KEEP_NULLS>;
+  const size_t smem_bytes = sizeof(Scatter32Smem);
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  int per_sm = 1;
+  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kS32Threads, smem_bytes));
+  const size_t tiles = (n + kS32Tile - 1) / kS32Tile;
+  const size_t cap = (size_t)sm_count() * (size_t)(per_sm > 0 ? per_sm : 1);  // exactly one resident wave
+  const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
+  {
+    B200_TIMED("join_part_scatter");
+    kern<<<sblocks, kS32Threads, smem_bytes>>>(keys, col->valid, n, g, d_cursors, out_pairs, payload, id_base);
+  }
+  B200_CHECK_LAST();
   return GDF_SUCCESS;
 }
 
@@ -992,7 +1133,7 @@ gdf_error partition_scatter(const gdf_column* col, PartGeom g, const unsigned lo
   const KT* keys = static_cast<const KT*>(col->data);
   const size_t n = col->size;
   B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  static const bool prefetch = getenv("B200_SCATTER_PREFETCH") ? atoi(getenv("B200_SCATTER_PREFETCH")) != 0 : false;
+  const bool prefetch = lab_knob("B200_SCATTER_PREFETCH", 0) != 0;
   auto kern = col2 ? part_scatter_kernel<KT, KEEP_NULLS, false, true>
                    : (prefetch ? part_scatter_kernel<KT, KEEP_NULLS, true, false> : part_scatter_kernel<KT, KEEP_NULLS, false, false>);
   const size_t smem_bytes = sizeof(ScatterSmem<KT>) + (col2 ? kScatterTile * sizeof(uint32_t) : 0);
@@ -1062,7 +1203,7 @@ gdf_error launch_probe_stream(const Pairs<KT>& pr, PartGeom g, const Tables& t, 
   const size_t tiles = (pr.n + kP2Tile - 1) / kP2Tile;
   const size_t resident = (size_t)sm_count() * 2;
   const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
-  static const int hint_mode = getenv("B200_PROBE_HINTS") ? atoi(getenv("B200_PROBE_HINTS")) : 7;
+  const int hint_mode = lab_knob("B200_PROBE_HINTS", 7);
   kern<<<blocks, kP2Threads, smem>>>(pr, g, t, op, ob, cursor, ticket, hint_mode);
   B200_CHECK_LAST();
   return GDF_SUCCESS;
@@ -1073,7 +1214,7 @@ gdf_error launch_probe(bool unique, bool write, const Pairs<KT>& pr, PartGeom g,
                        int32_t* ob, unsigned long long* cursor, unsigned* ticket, bool stream_ok) {
   if (pr.n == 0) return GDF_SUCCESS;
   B200_TIMED(write ? "join_part_probe" : "join_part_count");
-  static const bool force_v1 = getenv("B200_PROBE_V1") ? atoi(getenv("B200_PROBE_V1")) != 0 : true;  // lab knob; the one-tile-per-CTA kernel is the fastest measured so far (profiles/r01b)
+  const bool force_v1 = lab_knob("B200_PROBE_V1", 1) != 0;  // the one-tile-per-CTA kernel is the fastest measured for 16-byte slots (profiles/r01b)
   if (pr.rows != nullptr && stream_ok && !force_v1) {  // partitioned {key,tag} pairs: streaming kernel
     if (unique) {
       if (write) return launch_probe_stream<KT, LEFT_LIKE, true, true>(pr, g, t, op, ob, cursor, ticket);
@@ -1101,6 +1242,152 @@ void view_indices(gdf_column* c, int32_t* data, size_t n) {
   else gdf_column_view(c, data, nullptr, n, GDF_INT32);
 }
 
+// ---- compact path (join_compact.cuh): tables, build, probe, fix-up for {key32, tag32} pairs ----
+template <bool LEFT_LIKE, bool UNIQUE, int MODE>
+gdf_error launch_probe32(const Pairs32& pr, PartGeom g, const Tables32& t, const Probe32Out& out, unsigned blocks) {
+  auto kern = probe32_kernel<LEFT_LIKE, UNIQUE, MODE>;
+  const int smem = (int)probe32_smem_bytes();
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<blocks, kC32Threads, smem>>>(pr, g, t, out, (unsigned)lab_knob("B200_LAB_PROBE", 0));
+  B200_CHECK_LAST();
+  return GDF_SUCCESS;
+}
+
+gdf_error run_compact(int kind, bool flip, PartGeom g, const Pairs32& bp, const Pairs32& pp, const unsigned long long* h_btot,
+                      size_t build_rows, unsigned long long* d_toffset, unsigned* d_tmask, unsigned long long* d_cursor,
+                      int* d_flags, gdf_column* out_l, gdf_column* out_r) {
+  const bool left_like = kind != JOIN_INNER;
+  unsigned long long h_toffset[kMaxParts], total_slots = 0;
+  unsigned h_tmask[kMaxParts];
+  for (unsigned p = 0; p < g.nparts; ++p) {  // load factor <= 0.5, whole buckets
+    unsigned slots = pow2_at_least(h_btot[p] ? 2 * h_btot[p] : 4);
+    if (slots < 4) slots = 4;
+    h_toffset[p] = total_slots;
+    h_tmask[p] = slots - 1;
+    total_slots += slots;
+  }
+  B200_CUDA_TRY(cudaMemcpy(d_toffset, h_toffset, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  B200_CUDA_TRY(cudaMemcpy(d_tmask, h_tmask, g.nparts * sizeof(unsigned), cudaMemcpyHostToDevice));
+  Scratch table;
+  B200_CUDA_TRY(table.alloc(total_slots * sizeof(unsigned long long)));
+  {
+    B200_TIMED("join_table_init");
+    B200_CUDA_TRY(cudaMemsetAsync(table.ptr, 0xff, total_slots * sizeof(unsigned long long), 0));
+  }
+  Tables32 t{table.as<unsigned long long>(), d_toffset, d_tmask};
+  if (bp.n) {
+    B200_TIMED("join_part_build");
+    build32_kernel<<<(unsigned)((bp.n + kB32Tile - 1) / kB32Tile), kB32Threads>>>(bp, g, t, d_flags);
+    B200_CHECK_LAST();
+  }
+  int h_flags[2] = {0, 0};
+  B200_CUDA_TRY(cudaMemcpy(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
+  const bool unique = h_flags[0] == 0;
+  if (pp.n == 0 && kind != JOIN_FULL) {
+    view_indices(out_l, nullptr, 0);
+    view_indices(out_r, nullptr, 0);
+    return GDF_SUCCESS;
+  }
+  const size_t tiles = (pp.n + kC32Tile - 1) / kC32Tile;
+  size_t want = (tiles + kC32Warps - 1) / kC32Warps;
+  const size_t resident = (size_t)sm_count();  // one 512-thread CTA (128 KB of rings) per SM
+  unsigned blocks = (unsigned)(want < resident ? (want ? want : 1) : resident);
+  if (2u * blocks * kC32Warps > (unsigned)kFixCap) blocks = kFixCap / (2 * kC32Warps);
+  const unsigned warps = blocks * kC32Warps;
+
+  Probe32Out out{nullptr, nullptr, d_cursor, nullptr, nullptr};
+  gdf_error e = GDF_SUCCESS;
+  size_t capacity = pp.n;
+  if (!unique) {  // exact count instead of the reference's estimate / retry loop
+    B200_TIMED("join_part_count");
+    e = left_like ? launch_probe32<true, false, P32_COUNT>(pp, g, t, out, blocks)
+                  : launch_probe32<false, false, P32_COUNT>(pp, g, t, out, blocks);
+    if (e != GDF_SUCCESS) return e;
+    unsigned long long exact = 0;
+    if ((e = read_u64(d_cursor, &exact)) != GDF_SUCCESS) return e;
+    capacity = (size_t)exact;
+    B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), 0));
+  } else if (!left_like) {
+    capacity = pp.n + (size_t)2 * warps * kC32Chunk;  // every warp may leave two partly filled chunks behind
+  }
+  if (kind == JOIN_FULL) capacity += build_rows;
+  if (capacity == 0) {
+    view_indices(out_l, nullptr, 0);
+    view_indices(out_r, nullptr, 0);
+    return GDF_SUCCESS;
+  }
+  int32_t *op = nullptr, *ob = nullptr;
+  B200_RMM_TRY(output_alloc((void**)&op, capacity * sizeof(int32_t)));
+  if (output_alloc((void**)&ob, capacity * sizeof(int32_t)) != RMM_SUCCESS) {
+    rmmFree(op, 0);
+    return GDF_MEMORYMANAGER_ERROR;
+  }
+  out.probe = op;
+  out.build = ob;
+  unsigned long long found = 0;
+  Scratch holes, plan;
+  if (pp.n) {
+    if (!unique) {
+      B200_TIMED("join_part_probe");
+      e = left_like ? launch_probe32<true, false, P32_CURSOR>(pp, g, t, out, blocks)
+                    : launch_probe32<false, false, P32_CURSOR>(pp, g, t, out, blocks);
+      if (e == GDF_SUCCESS) e = read_u64(d_cursor, &found);
+    } else if (left_like) {  // one pair per probe row, at the row's own position
+      B200_TIMED("join_part_probe");
+      e = launch_probe32<true, true, P32_POSITIONAL>(pp, g, t, out, blocks);
+      found = pp.n;
+    } else {
+      cudaError_t ce = holes.alloc((size_t)2 * warps * (sizeof(unsigned long long) + sizeof(unsigned)));
+      if (ce == cudaSuccess) ce = plan.alloc(sizeof(FixPlan));
+      if (ce != cudaSuccess) e = GDF_CUDA_ERROR;
+      if (e == GDF_SUCCESS) {
+        out.hole_start = holes.as<unsigned long long>();
+        out.hole_len = reinterpret_cast<unsigned*>(out.hole_start + (size_t)2 * warps);
+        {
+          B200_TIMED("join_part_probe");
+          e = launch_probe32<false, true, P32_CHUNK>(pp, g, t, out, blocks);
+        }
+        if (e == GDF_SUCCESS) {
+          B200_TIMED("join_output_fixup");
+          const int fsmem = kFixCap * (int)(sizeof(unsigned long long) + 3 * sizeof(unsigned));
+          cudaFuncSetAttribute(fixup_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem);
+          fixup_plan_kernel<<<1, kFixThreads, fsmem>>>(out.hole_start, out.hole_len, 2 * warps, d_cursor, plan.as<FixPlan>());
+          fixup_move_kernel<<<sm_count() * 2, 256>>>(plan.as<FixPlan>(), op, ob);
+          if (cudaPeekAtLastError() != cudaSuccess) e = GDF_CUDA_ERROR;
+        }
+        if (e == GDF_SUCCESS) e = read_u64(&plan.as<FixPlan>()->found, &found);
+      }
+    }
+  }
+  if (e == GDF_SUCCESS && kind == JOIN_FULL) {
+    Scratch marks;
+    cudaError_t ce = marks.alloc(build_rows);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(marks.ptr, 0, build_rows, 0);
+    if (ce == cudaSuccess) {
+      ce = cudaMemcpy(d_cursor, &found, sizeof(unsigned long long), cudaMemcpyHostToDevice);  // append position
+    }
+    if (ce == cudaSuccess) {
+      if (found) mark_rows_kernel<<<grid_for((size_t)found), kThreads>>>(ob, (size_t)found, marks.as<unsigned char>(), build_rows);
+      append_unmatched_kernel<<<grid_for(build_rows), kThreads>>>(marks.as<unsigned char>(), build_rows, op, ob, d_cursor);
+      ce = cudaPeekAtLastError();
+    }
+    if (ce != cudaSuccess) e = GDF_CUDA_ERROR;
+    else e = read_u64(d_cursor, &found);
+  }
+  if (e != GDF_SUCCESS || found == 0) {
+    rmmFree(op, 0);
+    rmmFree(ob, 0);
+    if (e == GDF_SUCCESS) {
+      view_indices(out_l, nullptr, 0);
+      view_indices(out_r, nullptr, 0);
+    }
+    return e;
+  }
+  view_indices(flip ? out_r : out_l, op, (size_t)found);
+  view_indices(flip ? out_l : out_r, ob, (size_t)found);
+  return GDF_SUCCESS;
+}
+
 template <typename KT>
 gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_column* build_col, bool flip,
                           gdf_column* out_l, gdf_column* out_r, bool* handled, const int32_t* probe_payload,
@@ -1109,9 +1396,6 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   const bool left_like = kind != JOIN_INNER;
   PartGeom g;
   g.dest = 0;
-#ifdef B200_LAB_PROBE
-  if (getenv("B200_LAB_PROBE")) g.dest = (unsigned)atoi(getenv("B200_LAB_PROBE")) << 8;  // pid() tests dest & 1 only below
-#endif
   {
     unsigned np = pow2_at_least((B + kRowsPerPartition - 1) / kRowsPerPartition);
     if (np > kMaxParts) np = kMaxParts;
@@ -1120,17 +1404,17 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
     g.nparts = np;
     g.shift = 32 - lg;
   }
-  Scratch small;  // totals[np] | cursors[np] | toffset[np] | tmask[np] | cursor | flags
-  const size_t small_bytes = g.nparts * (3 * sizeof(unsigned long long) + sizeof(unsigned)) + 64;  // 64 = cursor|flags|ticket|pad
+  Scratch small;  // totals[np + 1] | cursors[np] | toffset[np] | cursor, flags, ticket (64 bytes) | tmask[np]
+  const size_t small_bytes = (g.nparts * 3 + 1) * sizeof(unsigned long long) + 64 + g.nparts * sizeof(unsigned);
   B200_CUDA_TRY(small.alloc(small_bytes));
   unsigned long long* d_totals = small.as<unsigned long long>();
-  unsigned long long* d_cursors = d_totals + g.nparts;
+  unsigned long long* d_cursors = d_totals + g.nparts + 1;
   unsigned long long* d_toffset = d_cursors + g.nparts;
   unsigned long long* d_cursor = d_toffset + g.nparts;
   int* d_flags = reinterpret_cast<int*>(d_cursor + 1);
   unsigned* d_ticket = reinterpret_cast<unsigned*>(d_cursor + 3);
-  unsigned* d_tmask = reinterpret_cast<unsigned*>(d_cursor + 4);
-  B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 4 * sizeof(unsigned long long), 0));
+  unsigned* d_tmask = reinterpret_cast<unsigned*>(d_cursor + 8);
+  B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 64, 0));
 
   Scratch bkeys, brows, pkeys, prows;
   // unpartitioned pairs: row tag = position, or the caller's payload (then masks are not supported)
@@ -1141,10 +1425,49 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   Scratch bk2, pk2;
   unsigned long long h_btot[kMaxParts];
   if (g.nparts > 1) {
-    unsigned long long h_ptot[kMaxParts];
-    size_t kept = 0;
-    gdf_error e = partition_side<KT, false>(build_col, g, bkeys, brows, d_totals, d_cursors, h_btot, &kept, build_payload, 0,
-                                            nullptr, nullptr, build_col2, &bk2);
+    unsigned long long h_ptot[kMaxParts], h_cursors[kMaxParts];
+    auto scan = [&](const unsigned long long* tot) {
+      unsigned long long run = 0;
+      for (unsigned p = 0; p < g.nparts; ++p) {
+        h_cursors[p] = run;
+        run += tot[p];
+      }
+      return (size_t)run;
+    };
+    // build-side histogram first: it also tells whether every valid build key fits 32 bits
+    unsigned hi_or = 0;
+    gdf_error e = partition_hist<KT, false>(build_col, g, d_totals, h_btot, build_col2, &hi_or);
+    if (e != GDF_SUCCESS) return e;
+    size_t kept = scan(h_btot);
+    bool compact = build_col2 == nullptr && (sizeof(KT) == 4 || hi_or == 0) && lab_knob("B200_JOIN_COMPACT", 1) != 0;
+    for (unsigned p = 0; p < g.nparts; ++p)
+      if (h_btot[p] > (1u << 22)) compact = false;  // the compact probe packs {partition, slot < 2^24} into 32 bits
+    if (compact) {
+      Scratch bpairs, ppairs;
+      B200_CUDA_TRY(bpairs.alloc((kept ? kept : 1) * sizeof(uint2)));
+      e = partition_scatter32<KT, false>(build_col, g, h_cursors, d_cursors, bpairs.as<uint2>(), build_payload, 0);
+      if (e != GDF_SUCCESS) return e;
+      const Pairs32 bp32{bpairs.as<uint2>(), kept};
+      e = left_like ? partition_hist<KT, true, true>(probe_col, g, d_totals, h_ptot)
+                    : partition_hist<KT, false, true>(probe_col, g, d_totals, h_ptot);
+      if (e != GDF_SUCCESS) return e;
+      kept = scan(h_ptot);
+      B200_CUDA_TRY(ppairs.alloc((kept ? kept : 1) * sizeof(uint2)));
+      e = left_like ? partition_scatter32<KT, true>(probe_col, g, h_cursors, d_cursors, ppairs.as<uint2>(), probe_payload, 0)
+                    : partition_scatter32<KT, false>(probe_col, g, h_cursors, d_cursors, ppairs.as<uint2>(), probe_payload, 0);
+      if (e != GDF_SUCCESS) return e;
+      const Pairs32 pp32{ppairs.as<uint2>(), kept};
+      *handled = true;
+      return run_compact(kind, flip, g, bp32, pp32, h_btot, B, d_toffset, d_tmask, d_cursor, d_flags, out_l, out_r);
+    }
+    // general path: {key, tag} (+ second key) in separate arrays, 16-byte slots
+    PeerDst none;
+    none.on = 0;
+    B200_CUDA_TRY(bkeys.alloc((kept ? kept : 1) * sizeof(KT)));
+    B200_CUDA_TRY(brows.alloc((kept ? kept : 1) * sizeof(int32_t)));
+    if (build_col2) B200_CUDA_TRY(bk2.alloc((kept ? kept : 1) * sizeof(uint32_t)));
+    e = partition_scatter<KT, false>(build_col, g, h_cursors, d_cursors, bkeys.as<KT>(), brows.as<int32_t>(), build_payload, 0,
+                                     none, build_col2, build_col2 ? bk2.as<uint32_t>() : nullptr);
     if (e != GDF_SUCCESS) return e;
     bp = Pairs<KT>{bkeys.as<KT>(), brows.as<int32_t>(), nullptr, kept, build_col2 ? bk2.as<uint32_t>() : nullptr, nullptr};
     e = left_like ? partition_side<KT, true>(probe_col, g, pkeys, prows, d_totals, d_cursors, h_ptot, &kept, probe_payload, 0,
@@ -1276,11 +1599,11 @@ gdf_error partition_pairs_typed(const gdf_column* key, int32_t id_base, unsigned
   g.shift = 0;
   g.dest = 1;
   Scratch small, unused_a, unused_b;
-  B200_CUDA_TRY(small.alloc(2 * (size_t)num_partitions * sizeof(unsigned long long)));
+  B200_CUDA_TRY(small.alloc((2 * (size_t)num_partitions + 1) * sizeof(unsigned long long)));
   unsigned long long h_tot[kMaxParts];
   size_t kept = 0;
   gdf_error e = partition_side<KT, false>(key, g, unused_a, unused_b, small.as<unsigned long long>(),
-                                          small.as<unsigned long long>() + num_partitions, h_tot, &kept, nullptr, id_base,
+                                          small.as<unsigned long long>() + num_partitions + 1, h_tot, &kept, nullptr, id_base,
                                           static_cast<KT*>(out_keys), out_ids);
   if (e != GDF_SUCCESS) return e;
   unsigned long long run = 0;
@@ -1300,7 +1623,7 @@ gdf_error partition_count(const gdf_column* key, unsigned num_partitions, unsign
   g.shift = 0;
   g.dest = 1;
   Scratch small;
-  B200_CUDA_TRY(small.alloc((size_t)num_partitions * sizeof(unsigned long long)));
+  B200_CUDA_TRY(small.alloc(((size_t)num_partitions + 1) * sizeof(unsigned long long)));
   switch (key->dtype) {
     case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
       return partition_hist<uint64_t, false>(key, g, small.as<unsigned long long>(), h_counts);

@@ -205,3 +205,64 @@ def test_partitioned_path_composite_key_same_first_key_different_second():
     probe[1][::3] = 0                                              # every third probe row matches
     check("inner", probe, build)
     check("left", probe, build)
+
+
+# ---- compact (32-bit key) path of the partitioned join: csrc/join_compact.cuh ----
+@pytest.mark.parametrize("kind", ["inner", "left", "full"])
+@pytest.mark.parametrize("hit", [0.0, 0.03, 1.0], ids=["nohit", "hit3pct", "allhit"])
+def test_compact_path_hit_rates(kind, hit):
+    """Unique build keys that fit 32 bits: INNER fills per-warp output chunks and the fix-up pass closes the holes
+    (0 % and 3 % hit rates leave almost every chunk nearly empty, 100 % fills them), LEFT/FULL write in place."""
+    nb, npr = 2_300_000, 4_100_003
+    build = (np.random.permutation(nb).astype(np.int64) * 3 + 1)
+    if hit == 0.0:
+        probe = np.random.randint(0, nb, npr).astype(np.int64) * 3               # never 1 mod 3
+    elif hit == 1.0:
+        probe = build[np.random.randint(0, nb, npr)]
+    else:
+        probe = np.random.randint(0, int(3 * nb / hit), npr).astype(np.int64)
+    check(kind, [probe], [build])
+
+
+@pytest.mark.parametrize("kind", ["inner", "left", "full"])
+def test_compact_path_probe_keys_wider_than_32_bits(kind):
+    """Build keys fit 32 bits, some probe keys do not (and some are negative): those rows can never match - INNER
+    drops them, LEFT/FULL emit (row,-1) - and must not alias a build key with the same low word."""
+    nb, npr = 1_400_000, 2_000_000
+    build = np.random.permutation(nb).astype(np.int64)
+    probe = np.random.randint(0, nb, npr).astype(np.int64)
+    probe[::5] += np.int64(1) << 32                    # same low word as a build key, different high word
+    probe[1::7] = -probe[1::7] - 1                     # negative: high word all ones
+    check(kind, [probe], [build])
+
+
+@pytest.mark.parametrize("kind", ["inner", "left"])
+def test_wide_build_keys_take_the_general_path(kind):
+    nb, npr = 1_400_000, 2_000_000
+    build = np.random.permutation(nb).astype(np.int64) + (np.int64(5) << 32)
+    build[::2] -= np.int64(5) << 32
+    probe = np.concatenate([build[np.random.randint(0, nb, npr // 2)], np.random.randint(0, nb, npr - npr // 2).astype(np.int64)])
+    check(kind, [probe], [build])
+
+
+@pytest.mark.parametrize("kind", ["inner", "left", "full"])
+def test_compact_path_int32_negative_keys_and_masks(kind):
+    nb, npr = 1_300_000, 1_900_000
+    build = (np.random.permutation(nb).astype(np.int32) - nb // 2)
+    probe = np.random.randint(-nb, nb, npr).astype(np.int32)
+    lv = [np.packbits(np.random.rand(npr) < 0.8, bitorder="little")]
+    rv = [np.packbits(np.random.rand(nb) < 0.9, bitorder="little")]
+    check(kind, [probe], [build], lv, rv)
+
+
+def test_compact_path_heavy_duplicates():
+    """A few build keys repeated thousands of times: chains span many buckets; exact count pass + write pass."""
+    nb, npr = 1_200_000, 6_000
+    build = np.random.randint(0, 300, nb).astype(np.int64)
+    probe = np.random.randint(0, 400, npr).astype(np.int64)
+    gl, gr = join("inner", [probe], [build])
+    counts = np.bincount(build, minlength=400)
+    assert len(gl) == int(counts[probe].sum())
+    assert np.array_equal(probe[gl], build[gr])
+    pairs = gl.astype(np.int64) * nb + gr
+    assert len(np.unique(pairs)) == len(pairs)
