@@ -28,6 +28,16 @@ const char * gdf_cuda_error_string(int cuda_error);
 const char * gdf_cuda_error_name(int cuda_error);
 gdf_error get_column_byte_width(gdf_column * col, int * width);
 
+/* ---- concatenation (ref functions.h:94, src/column.cpp:53-153, src/validops.cu:203-256): what a
+ * caller uses to stitch per-GPU shards of a column back together.  output->size must equal the sum of the input
+ * sizes and its buffers are caller-allocated; a column without mask counts as all valid.  gdf_mask_concat has no
+ * public prototype in the reference (column.cpp:29 declares it locally); masks_to_concat / column_lengths may be
+ * host, managed or device arrays. ---- */
+gdf_error gdf_column_concat(gdf_column *output, gdf_column *columns_to_concat[], int num_columns);
+gdf_error gdf_mask_concat(gdf_valid_type *output_mask, gdf_size_type output_column_length,
+                          gdf_valid_type *masks_to_concat[], gdf_size_type *column_lengths,
+                          gdf_size_type num_columns);
+
 /* ---- hash joins (ref functions.h:226-318, src/join/joining.cu:571-653).
  * Output index columns are allocated by the library with rmmAlloc and released by the caller with
  * gdf_column_free; unmatched side is -1; pair order is unspecified. ---- */
@@ -169,6 +179,11 @@ gdf_error gpu_comparison_static_f32(gdf_column *lhs, float value, gdf_column *ou
 gdf_error gpu_comparison_static_f64(gdf_column *lhs, double value, gdf_column *output, gdf_comparison_operator operation);
 gdf_error gpu_comparison(gdf_column *lhs, gdf_column *rhs, gdf_column *output, gdf_comparison_operator operation);
 gdf_error gpu_apply_stencil(gdf_column *lhs, gdf_column * stencil, gdf_column * output);
+
+/* ---- multi-column ORDER BY (ref functions.h:711-716, src/sqls_ops.cu:1373-1392).
+ * cols is a HOST array of gdf_column structs (no masks); d_cols/d_types are caller device scratch that the call
+ * fills; d_indx receives the row indices (size_t) in lexicographic ascending order of the columns. ---- */
+gdf_error gdf_order_by(size_t nrows, gdf_column* cols, size_t ncols, void** d_cols, int* d_types, size_t* d_indx);
 
 /* ---- multi-column WHERE (ref functions.h:718-725, src/sqls_ops.cu:1401-1424).
  * cols is a HOST array of gdf_column structs; d_cols/d_types are caller device scratch that the call

@@ -37,3 +37,9 @@ rmmError_t rmmGetInfo(size_t *freeSize, size_t *totalSize, cudaStream_t stream);
 rmmError_t rmmWriteLog(const char* filename);
 size_t rmmLogSize();
 rmmError_t rmmGetLog(char* buffer, size_t buffer_size);
+
+/* ---- extensions (not in the reference): the PoolAllocation cache of this implementation keeps freed blocks for
+ * reuse (csrc/block_cache.h); these two let a caller - and libgdf.so, before it reports out-of-memory for its own
+ * scratch - hand the cached blocks back to the driver and see how much is parked. ---- */
+void rmmxTrimPool(void);
+size_t rmmxPoolCachedBytes(void);

@@ -26,7 +26,9 @@
 #include <cstdlib>
 #include <limits>
 #include <type_traits>
+#include <vector>
 
+#include "sort.cuh"
 #include "table.cuh"
 
 namespace b200 {
@@ -484,8 +486,69 @@ gdf_error dispatch_fast_key(gdf_column* key, gdf_column* col_agg, int op, gdf_co
   return GDF_SUCCESS;
 }
 
+// Reorders the `groups` output rows (key columns + aggregate) into lexicographic key order.
+gdf_error sort_groups(int ncols, gdf_column** cols, gdf_column** out_vals, gdf_column* out_agg, int agg_dtype, size_t groups) {
+  B200_TIMED("groupby_sort_result");
+  std::vector<gdf_column> views((size_t)ncols);
+  std::vector<const gdf_column*> ptrs((size_t)ncols);
+  for (int c = 0; c < ncols; ++c) {  // the keys were copied bit for bit, so they order as the INPUT column's type
+    gdf_column_view(&views[c], out_vals[c]->data, nullptr, groups, cols[c]->dtype);
+    ptrs[c] = &views[c];
+  }
+  Scratch perm;
+  B200_CUDA_TRY(perm.alloc(groups * sizeof(uint32_t)));
+  gdf_error e = sort_permutation(ptrs.data(), ncols, groups, perm.as<uint32_t>());
+  for (int c = 0; c < ncols && e == GDF_SUCCESS; ++c)
+    e = permute_in_place(out_vals[c]->data, dtype_width(cols[c]->dtype), groups, perm.as<uint32_t>());
+  if (e == GDF_SUCCESS) e = permute_in_place(out_agg->data, dtype_width(agg_dtype), groups, perm.as<uint32_t>());
+  return e;
+}
+
+// order-preserving unsigned image of a typed value (the same map the radix sort uses, sort.cu)
+static __device__ __forceinline__ unsigned long long ordered_bits(int dtype, unsigned long long bits) {
+  const int w = dtype_width(dtype);
+  const unsigned long long sign = 1ull << (8 * w - 1);
+  const unsigned long long all = w == 8 ? ~0ull : ((1ull << (8 * (w & 7))) - 1ull);
+  if (dtype == GDF_FLOAT32 || dtype == GDF_FLOAT64) return (bits & sign) ? (~bits & all) : (bits | sign);
+  return bits ^ sign;
+}
+
+// Sort method: index of one row of every group (the smallest row id), groups given in sorted key order.
+// Every input row finds its group by binary search over the sorted group keys and lowers that group's entry.
+__global__ void __launch_bounds__(kThreads)
+group_rows_kernel(TableView in, TableView sorted_groups, unsigned long long* __restrict__ rep) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t r = (size_t)blockIdx.x * kThreads + threadIdx.x; r < in.rows; r += stride) {
+    size_t lo = 0, hi = sorted_groups.rows;  // first group whose key is >= row r's key
+    while (lo < hi) {
+      const size_t mid = (lo + hi) >> 1;
+      bool less = false;  // group[mid] < row r ?
+#pragma unroll 1
+      for (int c = 0; c < in.ncols; ++c) {
+        const unsigned long long a = ordered_bits(in.dtype[c], load_bits(sorted_groups, c, mid));
+        const unsigned long long b = ordered_bits(in.dtype[c], load_bits(in, c, r));
+        if (a != b) {
+          less = a < b;
+          break;
+        }
+      }
+      if (less) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < sorted_groups.rows) atomicMin(&rep[lo], (unsigned long long)r);
+  }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+template <typename T>
+__global__ void store_scalar_kernel(T* p, double v) { p[0] = (T)v; }
+
 gdf_error group_by_hash(int ncols, gdf_column** cols, gdf_column* col_agg, gdf_column** out_vals,
-                        gdf_column* out_agg, int op, bool /*sort_result*/) {
+                        gdf_column* out_agg, int op, bool sort_result) {
   if (ncols == 0 || cols == nullptr || col_agg == nullptr) return GDF_DATASET_EMPTY;
   if (out_vals == nullptr || out_agg == nullptr) return GDF_DATASET_EMPTY;
   if (cols[0]->size == 0 || col_agg->size == 0) return GDF_SUCCESS;
@@ -519,8 +582,81 @@ gdf_error group_by_hash(int ncols, gdf_column** cols, gdf_column* col_agg, gdf_c
     gdf_error e = dispatch_generic(keys, ko, col_agg, op, out_agg, &groups);
     if (e != GDF_SUCCESS) return e;
   }
+  if ((sort_result || op == OP_AVG) && groups > 1) {
+    // flag_sort_result: groups in lexicographic key order (ref groupby_compute_api.h:211-222); AVG always comes back
+    // sorted in the reference because its SUM and COUNT passes are matched up through sorted outputs (groupby.cuh:346-386)
+    gdf_error e = sort_groups(ncols, cols, out_vals, out_agg, op == OP_COUNT || op == OP_AVG ? out_agg->dtype : col_agg->dtype,
+                              groups);
+    if (e != GDF_SUCCESS) return e;
+  }
   for (int c = 0; c < ncols; ++c) out_vals[c]->size = groups;
   out_agg->size = groups;
+  return GDF_SUCCESS;
+}
+
+// GDF_SORT method (ref sqls_ops.cu:1134-1289, sqls_rtti_comp.hpp:372-640).  Observable contract of the reference:
+// groups come back in lexicographic key order; out_col_agg holds one aggregate per group; out_col_indices (if given)
+// holds, as size_t, the index of one row of each group (the reference returns whichever row its unstable sort put
+// first); out_col_values (if given) the group keys; flag_distinct with COUNT returns the NUMBER of groups in
+// out_col_agg[0] and size 1.  B200 design: sorting 1e9 rows only to reduce neighbouring runs moves every row through
+// ~8 radix passes; the same contract is met by the hash aggregation above followed by a sort of the (few) groups, and
+// the representative rows come from one binary-search pass over the input.  Floating-point sums differ from a
+// sort-and-reduce order within the tolerance stated in the tests (the reference's own order is not deterministic).
+gdf_error group_by_sort_method(int ncols, gdf_column** cols, gdf_column* col_agg, gdf_column* out_col_indices,
+                               gdf_column** out_col_values, gdf_column* out_col_agg, gdf_context* ctxt, int op) {
+  const size_t n = cols[0]->size;
+  B200_REQUIRE(ncols <= kMaxCols, GDF_JOIN_TOO_MANY_COLUMNS);
+  // group keys are needed internally even when the caller does not ask for them
+  std::vector<Scratch> tmp((size_t)ncols);
+  std::vector<gdf_column> tmp_cols((size_t)ncols);
+  std::vector<gdf_column*> key_out((size_t)ncols);
+  for (int c = 0; c < ncols; ++c) {
+    B200_REQUIRE(hashable_dtype(cols[c]->dtype), GDF_UNSUPPORTED_DTYPE);
+    if (out_col_values && out_col_values[c] && out_col_values[c]->data) {
+      key_out[c] = out_col_values[c];
+    } else {
+      B200_CUDA_TRY(tmp[c].alloc(n * (size_t)dtype_width(cols[c]->dtype)));
+      gdf_column_view(&tmp_cols[c], tmp[c].ptr, nullptr, n, cols[c]->dtype);
+      key_out[c] = &tmp_cols[c];
+    }
+  }
+  gdf_error e = group_by_hash(ncols, cols, col_agg, key_out.data(), out_col_agg, op, true);
+  if (e != GDF_SUCCESS) return e;
+  const size_t groups = out_col_agg->size;
+  if (out_col_values)
+    for (int c = 0; c < ncols; ++c)
+      if (out_col_values[c]) {
+        out_col_values[c]->dtype = cols[c]->dtype;  // multi_gather_host, sqls_ops.cu:145-165
+        out_col_values[c]->size = groups;
+      }
+  if (out_col_indices && out_col_indices->data && groups) {
+    unsigned long long* rep = static_cast<unsigned long long*>(out_col_indices->data);
+    fill_u64_kernel<<<grid_for(groups), kThreads>>>(rep, groups, ~0ull);
+    TableView in, sorted;
+    make_view(in, cols, ncols);
+    make_view(sorted, key_out.data(), ncols);
+    sorted.rows = groups;
+    for (int c = 0; c < ncols; ++c) sorted.dtype[c] = (unsigned char)cols[c]->dtype;
+    group_rows_kernel<<<grid_for(n), kThreads>>>(in, sorted, rep);
+    B200_CHECK_LAST();
+  }
+  if (out_col_indices) out_col_indices->size = groups;
+  if (op == OP_COUNT && ctxt->flag_distinct) {  // COUNT DISTINCT: one row holding the number of groups
+    switch (out_col_agg->dtype) {
+      case GDF_INT8: store_scalar_kernel<<<1, 1>>>(static_cast<int8_t*>(out_col_agg->data), (double)groups); break;
+      case GDF_INT16: store_scalar_kernel<<<1, 1>>>(static_cast<int16_t*>(out_col_agg->data), (double)groups); break;
+      case GDF_INT32: case GDF_DATE32: store_scalar_kernel<<<1, 1>>>(static_cast<int32_t*>(out_col_agg->data), (double)groups); break;
+      case GDF_FLOAT32: store_scalar_kernel<<<1, 1>>>(static_cast<float*>(out_col_agg->data), (double)groups); break;
+      case GDF_FLOAT64: store_scalar_kernel<<<1, 1>>>(static_cast<double*>(out_col_agg->data), (double)groups); break;
+      default: store_scalar_kernel<<<1, 1>>>(static_cast<int64_t*>(out_col_agg->data), (double)groups); break;
+    }
+    B200_CHECK_LAST();
+    out_col_agg->size = 1;
+    if (out_col_indices) out_col_indices->size = 1;
+    if (out_col_values)
+      for (int c = 0; c < ncols; ++c)
+        if (out_col_values[c]) out_col_values[c]->size = 1;
+  }
   return GDF_SUCCESS;
 }
 
@@ -538,13 +674,14 @@ gdf_error group_by_single(int ncols, gdf_column** cols, gdf_column* col_agg, gdf
         if (out_col_values[c]) out_col_values[c]->size = 0;
     return GDF_SUCCESS;
   }
-  if (ctxt->flag_method != GDF_HASH) return GDF_UNSUPPORTED_METHOD;  // sort-based group-by: see DESIGN.md
-  // The reference sorts the hash group-by's output by key when flag_sort_result is set
-  // (groupby_compute_api.h:211-222).  That sort is not implemented yet: refuse loudly instead of handing back
-  // groups in unspecified order to a caller that asked for a sorted result.
-  if (ctxt->flag_sort_result == 1) return GDF_UNSUPPORTED_METHOD;
+  if (ctxt->flag_method != GDF_HASH && ctxt->flag_method != GDF_SORT) return GDF_UNSUPPORTED_METHOD;
   gdf_nvtx_range_push("LIBGDF_GROUPBY", GDF_GREEN);
-  gdf_error e = group_by_hash(ncols, cols, col_agg, out_col_values, out_col_agg, op, ctxt->flag_sort_result == 1);
+  gdf_error e = GDF_SUCCESS;
+  if (ctxt->flag_method == GDF_HASH) {
+    e = group_by_hash(ncols, cols, col_agg, out_col_values, out_col_agg, op, ctxt->flag_sort_result == 1);
+  } else {
+    e = group_by_sort_method(ncols, cols, col_agg, out_col_indices, out_col_values, out_col_agg, ctxt, op);
+  }
   gdf_nvtx_range_pop();
   return e;
 }
@@ -568,6 +705,6 @@ B200_GROUPBY(avg, OP_AVG)
 extern "C" gdf_error gdf_group_by_count(int ncols, gdf_column** cols, gdf_column* col_agg,
                                         gdf_column* out_col_indices, gdf_column** out_col_values,
                                         gdf_column* out_col_agg, gdf_context* ctxt) {
-  if (ctxt && ctxt->flag_distinct) return GDF_UNSUPPORTED_METHOD;  // ref sqls_ops.cu:1357-1359 (hash path)
+  if (ctxt && ctxt->flag_distinct && ctxt->flag_method != GDF_SORT) return GDF_UNSUPPORTED_METHOD;  // ref sqls_ops.cu:1357-1359 (hash path)
   return group_by_single(ncols, cols, col_agg, out_col_indices, out_col_values, out_col_agg, ctxt, OP_COUNT);
 }

@@ -429,6 +429,311 @@ probe32_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, unsigned lab)
   }
 }
 
+// ---- probe, UNIQUE build keys (the PK/FK case, C3): the lean kernel ----
+// ncu on the first version of probe32_kernel at C3 (profiles/r02a_ncu_join_full.md): ~200 SASS instructions per row,
+// 17 % of them branch / reconvergence (BSSY, BSYNC, BRA) from per-row `if`s, stall_wait dominant with 4 warps per
+// scheduler - the kernel was bound by its own instruction stream.  With that fixed (8.7 ms) the ablations showed a
+// latency chain instead: look-ups alone +3.1 ms (= the L1TEX rate of one divergent sector per cycle per SM), but
+// look-ups AND stores +6.5 ms, because nearly every 256-row tile has a row whose home bucket is full of other keys
+// (~2 % of the rows), and the whole warp waited a second dependent L2 round trip for it.  This version:
+//   * a tile of 256 consecutive pairs lies inside ONE partition except at partition boundaries (the pairs are
+//     partition-contiguous), so the table base and mask are warp-uniform values found from the tile's position
+//     (part_start), not per-row shared-memory look-ups;
+//   * the bucket test is branch-free: first = row word of the slot whose key word equals the key, scanning from the
+//     last slot to the first (an EMPTY slot that happens to "match" key 0xffffffff yields row -1 = "no partner",
+//     which is the right answer, because slots fill in order and nothing real can follow an EMPTY slot);
+//     a row is settled when it found its partner or when the bucket's last slot is EMPTY;
+//   * unsettled rows are NOT waited for: they go to the warp's STRAGGLER QUEUE in shared memory ({key, tag,
+//     position, bucket number}), and up to 32 queued rows ride along with the NEXT tile as a ninth row - their next
+//     bucket is fetched together with that tile's home buckets.  A tile therefore costs one L2 round trip.  (If a
+//     tile ever produces more stragglers than the queue holds, that tile falls back to resolving in place.)
+//   * INNER: output positions from per-warp chunks as described above, with a branch-free fast path for tiles that
+//     do not cross a chunk boundary.  LEFT / FULL: one pair per row at the row's own position.
+constexpr unsigned kQCap = 128;   // straggler queue entries per warp (power of two)
+
+struct Probe32USmem {
+  uint64_t bar[kC32Warps][kC32Stages];
+  unsigned long long part_start[kMaxParts + 1];   // first pair of partition p in pr.pairs; [nparts] = pr.n
+  unsigned part_off[kMaxParts];                   // first slot of partition p (total slots < 2^32 on this path)
+  unsigned part_mask[kMaxParts];                  // (slots_p - 1) & ~3: bucket-aligned slot mask
+  uint4 queue[kC32Warps][kQCap];                  // .x key, .y tag, .z position in pr.pairs, .w bucket number to try next
+};
+constexpr size_t probe32u_smem_bytes() {
+  return (size_t)kC32Warps * kC32Stages * kC32Tile * sizeof(uint2) + sizeof(Probe32USmem) + 128;
+}
+
+template <bool LEFT_LIKE>
+__global__ void __launch_bounds__(kC32Threads, 1)
+probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const unsigned long long* __restrict__ part_start,
+                      unsigned lab) {
+  extern __shared__ __align__(128) unsigned char probe32u_smem[];
+  uint2* const ring_all = reinterpret_cast<uint2*>(probe32u_smem);
+  Probe32USmem& sm = *reinterpret_cast<Probe32USmem*>(probe32u_smem + (size_t)kC32Warps * kC32Stages * kC32Tile * sizeof(uint2));
+  const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const size_t tiles = (pr.n + kC32Tile - 1) / kC32Tile;
+  const size_t gw = (size_t)blockIdx.x * kC32Warps + warp;
+  const size_t W = (size_t)gridDim.x * kC32Warps;
+  uint2* const ring = ring_all + (size_t)warp * kC32Stages * kC32Tile;
+  uint64_t* const bar = sm.bar[warp];
+  uint4* const queue = sm.queue[warp];
+  uint64_t pol_stream, pol_table;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_table));
+  for (unsigned p = tid; p < g.nparts; p += kC32Threads) {
+    sm.part_off[p] = (unsigned)t.offset[p];
+    sm.part_mask[p] = t.mask[p] & ~3u;
+  }
+  for (unsigned p = tid; p <= g.nparts; p += kC32Threads) sm.part_start[p] = part_start[p];
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kC32Stages; ++s) tma::mbar_init(&bar[s], 1);
+    tma::fence_barrier_init();
+  }
+  __syncthreads();  // the only CTA-wide barrier
+
+  auto issue = [&](size_t it) {
+    const size_t tl = it * W + gw;
+    if (tl < tiles && (tl + 1) * kC32Tile <= pr.n) {
+      const int s = (int)(it % kC32Stages);
+      tma::mbar_expect_tx(&bar[s], kC32Tile * (uint32_t)sizeof(uint2));
+      bulk_load_policy(ring + (size_t)s * kC32Tile, pr.pairs + tl * kC32Tile, kC32Tile * (uint32_t)sizeof(uint2), &bar[s],
+                       pol_stream);
+    }
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kC32Stages; ++s) issue((size_t)s);
+  }
+  const unsigned lt_mask = lanemask_lt();
+  unsigned long long chunk_base = 0, next_base = 0;
+  unsigned chunk_used = kC32Chunk;  // "no chunk yet"
+  bool have_next = false;
+  unsigned cur_p = 0;               // partition of the current tile's first pair (tiles of a warp only move forward)
+  unsigned q_head = 0, q_count = 0; // straggler queue (warp-uniform)
+#ifdef B200_LAB
+  const bool no_lookup = (lab & 1u) != 0;     // ablation: no table look-up
+  const bool drop_stragglers = (lab & 4u) != 0;  // ablation: unsettled rows are forgotten
+#else
+  constexpr bool no_lookup = false, drop_stragglers = false;
+#endif
+  // absolute index of the first slot of bucket number `round` of key k (0 = home bucket), any partition
+  auto bucket_at = [&](uint32_t k, unsigned round) -> unsigned {
+    const uint32_t h = KeyBits<uint32_t>::hash(k);
+    const unsigned p = h >> g.shift;
+    return sm.part_off[p] + ((slot_hash(h) + 4u * round) & sm.part_mask[p]);
+  };
+  // first = row word of the slot holding k (or -1); settled = found, or the bucket's last slot is EMPTY
+  auto examine = [&](const Bucket32& b, uint32_t k, int32_t& f) -> bool {
+    f = -1;
+#pragma unroll
+    for (int j = 3; j >= 0; --j)
+      if ((uint32_t)b.w[j] == k) f = (int32_t)(uint32_t)(b.w[j] >> 32);
+    return f >= 0 || (uint32_t)(b.w[3] >> 32) == 0xffffffffu;
+  };
+
+  for (size_t it = 0;; ++it) {
+    const size_t tl = it * W + gw;
+    const bool has_tile = tl < tiles;
+    if (!has_tile && q_count == 0) break;   // after the last tile: extra iterations drain the queue
+    const size_t row0 = tl * kC32Tile;
+    const bool full = has_tile && row0 + kC32Tile <= pr.n;
+    const int s = (int)(it % kC32Stages);
+    if (!LEFT_LIKE && !have_next && chunk_used + (kC32Tile + 32) > kC32Chunk) {
+      // the tile (+ up to 32 queued rows) may overflow the current chunk: ask for the next one now, use it later
+      if (lane == 0) next_base = atomicAdd(out.cursor, (unsigned long long)kC32Chunk);
+      have_next = true;
+    }
+    bool one_part = false;
+    unsigned off_u = 0, mask_u = 0;
+    if (has_tile) {
+      while (row0 >= sm.part_start[cur_p + 1]) ++cur_p;
+      one_part = (full ? row0 + kC32Tile : pr.n) <= sm.part_start[cur_p + 1];
+      off_u = sm.part_off[cur_p];
+      mask_u = sm.part_mask[cur_p];
+    }
+    // The tile's pairs stay in the ring stage for the whole iteration and are re-read (LDS.64) where needed: holding
+    // 8 keys + 8 tags in registers across the bucket loads spilled (128-register budget at 512 threads).  The stage
+    // is handed back to the producer at the end of the iteration; three other stages are in flight meanwhile.
+    uint2* const stage = ring + (size_t)s * kC32Tile;
+    if (full) {
+      tma::mbar_wait(&bar[s], (unsigned)(it / kC32Stages) & 1u);
+    } else {  // ragged last tile / queue-draining iteration: no bulk copy was issued for this stage
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        const size_t j = row0 + i * 32 + lane;
+        uint2 v = make_uint2(0u, 0x80000000u);  // no row here: tag INT_MIN
+        if (has_tile && j < pr.n) v = pr.pairs[j];
+        stage[i * 32 + lane] = v;
+      }
+      __syncwarp();
+    }
+    auto pair_at = [&](int i) -> uint2 { return stage[i * 32 + lane]; };
+    // ---- all bucket loads of the iteration in flight: the tile's home buckets + one queued straggler per lane ----
+    Bucket32 bk[kC32Rows], qbk;
+    if (one_part) {  // warp-uniform: the common case gets its own straight-line code
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        const uint2 v = pair_at(i);
+        if ((int32_t)v.y >= 0 && !no_lookup)
+          bk[i] = ld_bucket32_hint(t.slots + (off_u + (slot_hash(KeyBits<uint32_t>::hash(v.x)) & mask_u)), pol_table);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        const uint2 v = pair_at(i);
+        if ((int32_t)v.y >= 0 && !no_lookup) bk[i] = ld_bucket32_hint(t.slots + bucket_at(v.x, 0), pol_table);
+      }
+    }
+    const unsigned take = q_count < 32u ? q_count : 32u;
+    const bool qlive = lane < take;
+    uint4 qe = make_uint4(0u, 0u, 0u, 0u);
+    if (qlive) {
+      qe = queue[(q_head + lane) & (kQCap - 1)];
+      qbk = ld_bucket32_hint(t.slots + bucket_at(qe.x, qe.w), pol_table);
+    }
+    q_head += take;
+    q_count -= take;
+    // ---- examine ----
+    int32_t first[kC32Rows], qfirst = -1;
+    unsigned pend = 0;   // bit i: row i is unsettled (goes to the queue)
+    unsigned live = 0;   // bit i: row i exists (tag != INT_MIN)
+#pragma unroll
+    for (int i = 0; i < kC32Rows; ++i) {
+      const uint2 v = pair_at(i);
+      int32_t f;
+      const bool settled = examine(bk[i], v.x, f);
+      const bool look = (int32_t)v.y >= 0 && !no_lookup;
+      first[i] = look ? f : (no_lookup && (int32_t)v.y >= 0 ? 0 : -1);
+      if (look && !settled) pend |= 1u << i;
+      if (v.y != 0x80000000u) live |= 1u << i;
+    }
+    bool qpend = false;
+    if (qlive) qpend = !examine(qbk, qe.x, qfirst);
+    if (drop_stragglers) { pend = 0; qpend = false; }
+    // ---- unsettled rows go (back) to the queue; if they do not fit, this tile's rows are resolved in place ----
+    {
+      unsigned need = __popc(__ballot_sync(0xffffffffu, qpend));
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) need += __popc(__ballot_sync(0xffffffffu, (pend >> i) & 1u));
+      if (need) {
+        if (q_count + need > kQCap) {  // does not fit (pathological collisions): blocking rounds for the tile's rows
+          for (unsigned round = 1; __any_sync(0xffffffffu, pend != 0); ++round) {
+#pragma unroll
+            for (int i = 0; i < kC32Rows; ++i)
+              if ((pend >> i) & 1u) bk[i] = ld_bucket32_hint(t.slots + bucket_at(pair_at(i).x, round), pol_table);
+#pragma unroll
+            for (int i = 0; i < kC32Rows; ++i) {
+              if (!((pend >> i) & 1u)) continue;
+              if (examine(bk[i], pair_at(i).x, first[i])) pend &= ~(1u << i);
+            }
+          }
+        }
+        unsigned tail = q_head + q_count;
+        {  // queued rows that are still unsettled: next bucket
+          const unsigned b = __ballot_sync(0xffffffffu, qpend);
+          if (qpend) queue[(tail + __popc(b & lt_mask)) & (kQCap - 1)] = make_uint4(qe.x, qe.y, qe.z, qe.w + 1u);
+          tail += __popc(b);
+        }
+#pragma unroll
+        for (int i = 0; i < kC32Rows; ++i) {
+          const unsigned b = __ballot_sync(0xffffffffu, (pend >> i) & 1u);
+          if (!b) continue;  // warp-uniform
+          if ((pend >> i) & 1u) {
+            const uint2 v = pair_at(i);
+            queue[(tail + __popc(b & lt_mask)) & (kQCap - 1)] = make_uint4(v.x, v.y, (uint32_t)(row0 + i * 32 + lane), 1u);
+          }
+          tail += __popc(b);
+        }
+        q_count = tail - q_head;
+        __syncwarp();
+      }
+    }
+    const bool qdone = qlive && !qpend;   // a queued row that is settled now (found or proven absent)
+    if (LEFT_LIKE) {  // exactly one pair per row, at the row's own position; queued rows are written when settled
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        if (((live >> i) & 1u) && !((pend >> i) & 1u)) {
+          const size_t j = row0 + i * 32 + lane;
+          const int32_t tg = (int32_t)pair_at(i).y;
+          st_i32_stream(out.probe + j, tg >= 0 ? tg : ~tg, pol_stream);
+          st_i32_stream(out.build + j, first[i], pol_stream);
+        }
+      }
+      if (qdone) {
+        st_i32_stream(out.probe + qe.z, (int32_t)qe.y, pol_stream);
+        st_i32_stream(out.build + qe.z, qfirst, pol_stream);
+      }
+    } else {
+      // ---- INNER: ranks from ballots, positions from the warp's chunk ----
+      unsigned rank[kC32Rows], qrank, total = 0;
+#pragma unroll
+      for (int i = 0; i < kC32Rows; ++i) {
+        if ((pend >> i) & 1u) first[i] = -1;   // queued: emitted later
+        const unsigned b = __ballot_sync(0xffffffffu, first[i] >= 0);
+        rank[i] = total + __popc(b & lt_mask);
+        total += __popc(b);
+      }
+      {
+        const unsigned b = __ballot_sync(0xffffffffu, qdone && qfirst >= 0);
+        qrank = total + __popc(b & lt_mask);
+        total += __popc(b);
+      }
+#ifdef B200_LAB
+      if (lab & 2u) total = 0;   // ablation: no output stores
+#endif
+      if (total == 0) {
+      } else if (chunk_used + total <= kC32Chunk) {  // the iteration's pairs fit the current chunk
+        int32_t* const po = out.probe + (chunk_base + chunk_used);
+        int32_t* const bo = out.build + (chunk_base + chunk_used);
+        chunk_used += total;
+#pragma unroll
+        for (int i = 0; i < kC32Rows; ++i) {
+          if (first[i] >= 0) {
+            st_i32_stream(po + rank[i], (int32_t)pair_at(i).y, pol_stream);
+            st_i32_stream(bo + rank[i], first[i], pol_stream);
+          }
+        }
+        if (qdone && qfirst >= 0) {
+          st_i32_stream(po + qrank, (int32_t)qe.y, pol_stream);
+          st_i32_stream(bo + qrank, qfirst, pol_stream);
+        }
+      } else {  // split: the first in_old pairs finish the current chunk, the rest start the next one
+        const unsigned in_old = kC32Chunk - chunk_used;
+        const unsigned long long old_at = chunk_base + chunk_used;
+        const unsigned long long new_base = __shfl_sync(0xffffffffu, next_base, 0);
+        chunk_base = new_base;
+        chunk_used = total - in_old;
+        have_next = false;
+        auto place = [&](unsigned r) -> size_t { return r < in_old ? (size_t)(old_at + r) : (size_t)(new_base + (r - in_old)); };
+#pragma unroll
+        for (int i = 0; i < kC32Rows; ++i) {
+          if (first[i] < 0) continue;
+          const size_t pos = place(rank[i]);
+          st_i32_stream(out.probe + pos, (int32_t)pair_at(i).y, pol_stream);
+          st_i32_stream(out.build + pos, first[i], pol_stream);
+        }
+        if (qdone && qfirst >= 0) {
+          const size_t pos = place(qrank);
+          st_i32_stream(out.probe + pos, (int32_t)qe.y, pol_stream);
+          st_i32_stream(out.build + pos, qfirst, pol_stream);
+        }
+      }
+    }
+    // ---- every lane is done with the stage: hand it back to the producer ----
+    __syncwarp();
+    if (full && lane == 0) {
+      tma::fence_proxy_async();
+      issue(it + kC32Stages);
+    }
+  }
+  if (!LEFT_LIKE && lane == 0) {  // what this warp reserved and did not fill
+    out.hole_start[2 * gw] = chunk_base + chunk_used;
+    out.hole_len[2 * gw] = kC32Chunk - chunk_used;
+    out.hole_start[2 * gw + 1] = next_base;
+    out.hole_len[2 * gw + 1] = have_next ? kC32Chunk : 0u;
+  }
+}
+
 // ---- fix-up of the chunked output: move the tail into the holes ----
 // plan kernel (one CTA): sorts the holes by position, computes found = allocated - sum(hole lengths), and two
 // segment lists with exclusive prefix sums: RECEIVERS = hole positions below `found`, DONORS = filled positions at or

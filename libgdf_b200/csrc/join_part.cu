@@ -1253,9 +1253,21 @@ gdf_error launch_probe32(const Pairs32& pr, PartGeom g, const Tables32& t, const
   return GDF_SUCCESS;
 }
 
+template <bool LEFT_LIKE>
+gdf_error launch_probe32_unique(const Pairs32& pr, PartGeom g, const Tables32& t, const Probe32Out& out,
+                                const unsigned long long* d_pstart, unsigned blocks) {
+  auto kern = probe32_unique_kernel<LEFT_LIKE>;
+  const int smem = (int)probe32u_smem_bytes();
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<blocks, kC32Threads, smem>>>(pr, g, t, out, d_pstart, (unsigned)lab_knob("B200_LAB_PROBE", 0));
+  B200_CHECK_LAST();
+  return GDF_SUCCESS;
+}
+
+// d_pstart: device array [nparts + 1], first pair of every partition in pp.pairs (last entry = pp.n)
 gdf_error run_compact(int kind, bool flip, PartGeom g, const Pairs32& bp, const Pairs32& pp, const unsigned long long* h_btot,
                       size_t build_rows, unsigned long long* d_toffset, unsigned* d_tmask, unsigned long long* d_cursor,
-                      int* d_flags, gdf_column* out_l, gdf_column* out_r) {
+                      int* d_flags, const unsigned long long* d_pstart, gdf_column* out_l, gdf_column* out_r) {
   const bool left_like = kind != JOIN_INNER;
   unsigned long long h_toffset[kMaxParts], total_slots = 0;
   unsigned h_tmask[kMaxParts];
@@ -1270,15 +1282,32 @@ gdf_error run_compact(int kind, bool flip, PartGeom g, const Pairs32& bp, const 
   B200_CUDA_TRY(cudaMemcpy(d_tmask, h_tmask, g.nparts * sizeof(unsigned), cudaMemcpyHostToDevice));
   Scratch table;
   B200_CUDA_TRY(table.alloc(total_slots * sizeof(unsigned long long)));
-  {
-    B200_TIMED("join_table_init");
-    B200_CUDA_TRY(cudaMemsetAsync(table.ptr, 0xff, total_slots * sizeof(unsigned long long), 0));
-  }
   Tables32 t{table.as<unsigned long long>(), d_toffset, d_tmask};
-  if (bp.n) {
+  {
+    // Tables are initialised and filled a few partitions at a time (<= 48 MB of slots per round): the EMPTY pattern
+    // written by the memset is still in L2 when the inserts arrive, so a bucket fetch is an L2 hit instead of a random
+    // 32-byte DRAM read (ncu, one memset + one build launch: 2.9 GB read + 1.6 GB written by the build kernel, 2.85 ms,
+    // latency-bound on those misses), and every table sector goes to DRAM once instead of twice.
     B200_TIMED("join_part_build");
-    build32_kernel<<<(unsigned)((bp.n + kB32Tile - 1) / kB32Tile), kB32Threads>>>(bp, g, t, d_flags);
-    B200_CHECK_LAST();
+    constexpr unsigned long long kRoundSlots = (48ull << 20) / sizeof(unsigned long long);
+    unsigned long long pair_lo = 0;
+    for (unsigned p = 0; p < g.nparts;) {
+      unsigned q = p;
+      unsigned long long slots = 0, pairs = 0;
+      do {
+        slots += (unsigned long long)h_tmask[q] + 1;
+        pairs += h_btot[q];
+        ++q;
+      } while (q < g.nparts && slots + h_tmask[q] + 1 <= kRoundSlots);
+      B200_CUDA_TRY(cudaMemsetAsync(t.slots + h_toffset[p], 0xff, slots * sizeof(unsigned long long), 0));
+      if (pairs) {
+        const Pairs32 part{bp.pairs + pair_lo, (size_t)pairs};
+        build32_kernel<<<(unsigned)((pairs + kB32Tile - 1) / kB32Tile), kB32Threads>>>(part, g, t, d_flags);
+        B200_CHECK_LAST();
+      }
+      pair_lo += pairs;
+      p = q;
+    }
   }
   int h_flags[2] = {0, 0};
   B200_CUDA_TRY(cudaMemcpy(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
@@ -1334,7 +1363,7 @@ gdf_error run_compact(int kind, bool flip, PartGeom g, const Pairs32& bp, const 
       if (e == GDF_SUCCESS) e = read_u64(d_cursor, &found);
     } else if (left_like) {  // one pair per probe row, at the row's own position
       B200_TIMED("join_part_probe");
-      e = launch_probe32<true, true, P32_POSITIONAL>(pp, g, t, out, blocks);
+      e = launch_probe32_unique<true>(pp, g, t, out, d_pstart, blocks);
       found = pp.n;
     } else {
       cudaError_t ce = holes.alloc((size_t)2 * warps * (sizeof(unsigned long long) + sizeof(unsigned)));
@@ -1345,7 +1374,7 @@ gdf_error run_compact(int kind, bool flip, PartGeom g, const Pairs32& bp, const 
         out.hole_len = reinterpret_cast<unsigned*>(out.hole_start + (size_t)2 * warps);
         {
           B200_TIMED("join_part_probe");
-          e = launch_probe32<false, true, P32_CHUNK>(pp, g, t, out, blocks);
+          e = launch_probe32_unique<false>(pp, g, t, out, d_pstart, blocks);
         }
         if (e == GDF_SUCCESS) {
           B200_TIMED("join_output_fixup");
@@ -1404,8 +1433,8 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
     g.nparts = np;
     g.shift = 32 - lg;
   }
-  Scratch small;  // totals[np + 1] | cursors[np] | toffset[np] | cursor, flags, ticket (64 bytes) | tmask[np]
-  const size_t small_bytes = (g.nparts * 3 + 1) * sizeof(unsigned long long) + 64 + g.nparts * sizeof(unsigned);
+  Scratch small;  // totals[np + 1] | cursors[np] | toffset[np] | cursor, flags, ticket (64 bytes) | pstart[np + 1] | tmask[np]
+  const size_t small_bytes = (g.nparts * 4 + 2) * sizeof(unsigned long long) + 64 + g.nparts * sizeof(unsigned);
   B200_CUDA_TRY(small.alloc(small_bytes));
   unsigned long long* d_totals = small.as<unsigned long long>();
   unsigned long long* d_cursors = d_totals + g.nparts + 1;
@@ -1413,7 +1442,8 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   unsigned long long* d_cursor = d_toffset + g.nparts;
   int* d_flags = reinterpret_cast<int*>(d_cursor + 1);
   unsigned* d_ticket = reinterpret_cast<unsigned*>(d_cursor + 3);
-  unsigned* d_tmask = reinterpret_cast<unsigned*>(d_cursor + 8);
+  unsigned long long* d_pstart = d_cursor + 8;
+  unsigned* d_tmask = reinterpret_cast<unsigned*>(d_pstart + g.nparts + 1);
   B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 64, 0));
 
   Scratch bkeys, brows, pkeys, prows;
@@ -1425,7 +1455,7 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   Scratch bk2, pk2;
   unsigned long long h_btot[kMaxParts];
   if (g.nparts > 1) {
-    unsigned long long h_ptot[kMaxParts], h_cursors[kMaxParts];
+    unsigned long long h_ptot[kMaxParts], h_cursors[kMaxParts + 1];
     auto scan = [&](const unsigned long long* tot) {
       unsigned long long run = 0;
       for (unsigned p = 0; p < g.nparts; ++p) {
@@ -1440,8 +1470,12 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
     if (e != GDF_SUCCESS) return e;
     size_t kept = scan(h_btot);
     bool compact = build_col2 == nullptr && (sizeof(KT) == 4 || hi_or == 0) && lab_knob("B200_JOIN_COMPACT", 1) != 0;
-    for (unsigned p = 0; p < g.nparts; ++p)
+    unsigned long long slots32 = 0;
+    for (unsigned p = 0; p < g.nparts; ++p) {
       if (h_btot[p] > (1u << 22)) compact = false;  // the compact probe packs {partition, slot < 2^24} into 32 bits
+      slots32 += pow2_at_least(h_btot[p] ? 2 * h_btot[p] : 4);
+    }
+    if (slots32 >= (1ull << 32) - 8) compact = false;  // absolute slot indices are 32-bit in the lean probe
     if (compact) {
       Scratch bpairs, ppairs;
       B200_CUDA_TRY(bpairs.alloc((kept ? kept : 1) * sizeof(uint2)));
@@ -1457,8 +1491,10 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
                     : partition_scatter32<KT, false>(probe_col, g, h_cursors, d_cursors, ppairs.as<uint2>(), probe_payload, 0);
       if (e != GDF_SUCCESS) return e;
       const Pairs32 pp32{ppairs.as<uint2>(), kept};
+      h_cursors[g.nparts] = kept;  // h_cursors = first pair of every probe partition
+      B200_CUDA_TRY(cudaMemcpy(d_pstart, h_cursors, (g.nparts + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
       *handled = true;
-      return run_compact(kind, flip, g, bp32, pp32, h_btot, B, d_toffset, d_tmask, d_cursor, d_flags, out_l, out_r);
+      return run_compact(kind, flip, g, bp32, pp32, h_btot, B, d_toffset, d_tmask, d_cursor, d_flags, d_pstart, out_l, out_r);
     }
     // general path: {key, tag} (+ second key) in separate arrays, 16-byte slots
     PeerDst none;

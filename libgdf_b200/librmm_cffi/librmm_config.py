@@ -1,7 +1,8 @@
 """Run-time configuration read by ``librmm.initialize()`` (reference:
 libgdf/python/librmm_cffi/librmm_config.py).  Set these before importing ``librmm_cffi``."""
 
-# False: cudaMalloc/cudaFree per allocation.  True: stream-ordered pool (cudaMallocAsync).
+# False: cudaMalloc/cudaFree per allocation.  True: caching pool (csrc/block_cache.h): freed blocks are kept and
+# reused, stream-aware like the reference's cnmem pool; librmm.finalize() / rmmxTrimPool() give them back.
 use_pool_allocator = False
 
 # Bytes reserved up front when the pool allocator is on; 0 = grow on demand.

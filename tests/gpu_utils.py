@@ -77,8 +77,10 @@ GROUPBY_FN = {"sum": "gdf_group_by_sum", "min": "gdf_group_by_min", "max": "gdf_
               "avg": "gdf_group_by_avg", "count": "gdf_group_by_count"}
 
 
-def groupby(op, key_cols, values, out_np_dtype=None, api=None, key_dtypes=None, sort_result=0):
-    """Call gdf_group_by_<op> (HASH); returns (list of key arrays, agg array) trimmed to the group count."""
+def groupby(op, key_cols, values, out_np_dtype=None, api=None, key_dtypes=None, sort_result=0, method="GDF_HASH",
+            distinct=0, want_indices=False):
+    """Call gdf_group_by_<op>; returns (list of key arrays, agg array) trimmed to the group count, in the order
+    the library wrote them (+ the out_col_indices array, size_t, with want_indices)."""
     api = api or libgdf
     n = len(values)
     key_dtypes = key_dtypes or [None] * len(key_cols)
@@ -88,17 +90,22 @@ def groupby(op, key_cols, values, out_np_dtype=None, api=None, key_dtypes=None, 
         out_np_dtype = values.dtype
     OK = [C.empty_column(n, K[i].data.dtype, dtype=key_dtypes[i], api=api) for i in range(len(K))]
     OA = C.empty_column(n, getattr(torch, np.dtype(out_np_dtype).name), api=api)
+    OI = C.empty_column(n, torch.int64, api=api) if want_indices else None
     ctx = ffi.new("gdf_context*")
-    api.gdf_context_view(ctx, 0, api.GDF_HASH, 0, sort_result, 0)
+    api.gdf_context_view(ctx, 0, getattr(api, method), distinct, sort_result, 0)
     ka, oka = C.column_array(K), C.column_array(OK)
-    err = getattr(api, GROUPBY_FN[op])(len(K), ka, V.cdata, ffi.NULL, oka, OA.cdata, ctx)
+    err = getattr(api, GROUPBY_FN[op])(len(K), ka, V.cdata, OI.cdata if OI else ffi.NULL, oka, OA.cdata, ctx)
     if err not in (None, 0):
         raise RuntimeError("%s -> %r" % (GROUPBY_FN[op], err))
     torch.cuda.synchronize()
     g = int(OA.cdata.size)
     for o in OK:
         assert int(o.cdata.size) == g
-    return [o.data[:g].cpu().numpy() for o in OK], OA.data[:g].cpu().numpy()
+    keys, agg = [o.data[:g].cpu().numpy() for o in OK], OA.data[:g].cpu().numpy()
+    if want_indices:
+        assert int(OI.cdata.size) == g
+        return keys, agg, OI.data[:g].cpu().numpy()
+    return keys, agg
 
 
 def rows_as_sorted_tuples(key_arrays, agg):
