@@ -437,6 +437,165 @@ class FilterWorkload(object):
         return ok and bool((idx[1:] > idx[:-1]).all())
 
 
+class StencilWorkload(object):
+    name = "C2 variant: gpu_comparison_static_i64(== 3) + gpu_apply_stencil, 1e9 int64 rows, 10 % selectivity"
+
+    def __init__(self, api, scale):
+        self.api = api
+        self.N = int(1e9 * scale)
+        self.col = torch.randint(0, 10, (self.N,), generator=gen(5), device="cuda", dtype=torch.int64)
+        self.stencil = torch.empty(self.N, dtype=torch.int8, device="cuda")
+        self.svalid = torch.empty((self.N + 7) // 8, dtype=torch.uint8, device="cuda")
+        self.out = torch.empty(self.N, dtype=torch.int64, device="cuda")      # the reference contract: output at input size
+        self.ovalid = torch.empty((self.N + 7) // 8, dtype=torch.uint8, device="cuda")
+        self.rows_per_step = self.N
+        self.selected = None
+
+    def _col(self, data, valid, code):
+        ffi, lib = self.api.ffi, self.api.lib
+        c = ffi.new("gdf_column*")
+        lib.gdf_column_view(c, ffi.cast("void*", data.data_ptr()), ffi.cast("gdf_valid_type*", valid.data_ptr()) if valid is not None else ffi.NULL,
+                            data.numel(), code)
+        return c
+
+    def step(self):
+        lib = self.api.lib
+        col = self._col(self.col, None, lib.GDF_INT64)
+        st = self._col(self.stencil, self.svalid, lib.GDF_INT8)
+        out = self._col(self.out, self.ovalid, lib.GDF_INT64)
+        self.api.check(lib.gpu_comparison_static_i64(col, 3, st, lib.GDF_EQUALS), "gpu_comparison_static_i64")
+        self.api.check(lib.gpu_apply_stencil(col, st, out), "gpu_apply_stencil")
+        self.selected = int(out.size)
+
+    def algorithmic_bytes(self):  # same figure as gdf_filter - the intermediate stencil traffic is not algorithmic
+        return 8 * self.N + 8 * self.selected
+
+    def check(self):
+        self.step()
+        k = self.selected
+        return k == int((self.col == 3).sum().item()) and bool((self.out[:k] == 3).all())
+
+
+class ReduceWorkload(object):
+    def __init__(self, api, scale, masked):
+        self.api, self.masked = api, masked
+        self.N = int(1e9 * scale)
+        self.name = "a15 gdf_sum_i64 over %.0e int64 rows%s" % (self.N, " with a 30 %-null validity mask" if masked else "")
+        self.col = torch.randint(-1000, 1000, (self.N,), generator=gen(6), device="cuda", dtype=torch.int64)
+        self.valid = None
+        if masked:
+            self.valid = torch.randint(0, 256, ((self.N + 7) // 8,), generator=gen(7), device="cuda", dtype=torch.uint8)
+            self.valid &= torch.randint(0, 256, ((self.N + 7) // 8,), generator=gen(8), device="cuda", dtype=torch.uint8)
+            self.valid |= torch.randint(0, 256, ((self.N + 7) // 8,), generator=gen(9), device="cuda", dtype=torch.uint8)  # P(bit) = 5/8
+        self.scratch = torch.zeros(int(api.lib.gdf_reduce_optimal_output_size()), dtype=torch.int64, device="cuda")
+        self.rows_per_step = self.N
+
+    def step(self):
+        ffi, lib = self.api.ffi, self.api.lib
+        c = ffi.new("gdf_column*")
+        lib.gdf_column_view(c, ffi.cast("void*", self.col.data_ptr()),
+                            ffi.cast("gdf_valid_type*", self.valid.data_ptr()) if self.valid is not None else ffi.NULL, self.N, lib.GDF_INT64)
+        self.api.check(lib.gdf_sum_i64(c, ffi.cast("int64_t*", self.scratch.data_ptr()), self.scratch.numel()), "gdf_sum_i64")
+
+    def algorithmic_bytes(self):  # (8 B + 1 bit) per row
+        return 8 * self.N + (self.N // 8 if self.masked else 0)
+
+    def check(self):
+        self.step()
+        got = int(self.scratch[0].item())
+        if not self.masked:
+            return got == int(self.col.sum().item())
+        want, chunk = 0, 1 << 27                                    # expand the bitmask in pieces (test-side only)
+        shifts = torch.arange(8, device="cuda", dtype=torch.uint8)
+        for lo in range(0, self.N, chunk):
+            hi = min(self.N, lo + chunk)
+            bits = ((self.valid[lo // 8:(hi + 7) // 8].unsqueeze(1) >> shifts) & 1).flatten()[: hi - lo].bool()
+            want += int(self.col[lo:hi][bits].sum().item())
+        return got == want
+
+
+class C5Workload(object):
+    name = "C5 gdf_left_join composite (int64,int32) key, 30 % null rows, 5e8 x 5e7"
+
+    def __init__(self, api, scale):
+        self.api = api
+        self.NL, self.NR = int(5e8 * scale), int(5e7 * scale)
+
+        def side(n, seed):
+            g = gen(seed)
+            k0 = torch.randint(0, self.NR, (n,), generator=g, device="cuda", dtype=torch.int64)
+            k1 = torch.randint(0, 4, (n,), generator=g, device="cuda", dtype=torch.int32)
+            null_row = torch.rand(n, generator=g, device="cuda") < 0.3
+            which = torch.rand(n, generator=g, device="cuda") < 0.5
+            return k0, k1, ~(null_row & which), ~(null_row & ~which)
+        self.l0, self.l1, self.lv0, self.lv1 = side(self.NL, 100)
+        self.r0, self.r1, self.rv0, self.rv1 = side(self.NR, 200)
+        self.lm, self.rm = [pack_bits(self.lv0), pack_bits(self.lv1)], [pack_bits(self.rv0), pack_bits(self.rv1)]
+        ffi, lib = api.ffi, api.lib
+        self.ctx = ffi.new("gdf_context*")
+        lib.gdf_context_view(self.ctx, 0, lib.GDF_HASH, 0, 0, 0)
+        self.idx = ffi.new("int[]", [0, 1])
+        self.out_l, self.out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
+        self.rows_per_step = self.NL + self.NR
+        self.pairs = None
+
+    def _cols(self, k0, k1, masks):
+        ffi, lib = self.api.ffi, self.api.lib
+        cols = []
+        for t, m, code in ((k0, masks[0], lib.GDF_INT64), (k1, masks[1], lib.GDF_INT32)):
+            c = ffi.new("gdf_column*")
+            lib.gdf_column_view_augmented(c, ffi.cast("void*", t.data_ptr()), ffi.cast("gdf_valid_type*", m.data_ptr()), t.numel(), code, 1)
+            cols.append(c)
+        return cols, ffi.new("gdf_column*[]", cols)
+
+    def call(self):
+        ffi, lib = self.api.ffi, self.api.lib
+        lk, la = self._cols(self.l0, self.l1, self.lm)
+        rk, ra = self._cols(self.r0, self.r1, self.rm)
+        self.api.check(lib.gdf_left_join(la, 2, self.idx, ra, 2, self.idx, 2, 0, ffi.NULL, self.out_l, self.out_r, self.ctx), "gdf_left_join")
+        self.pairs = int(self.out_l.size)
+
+    def free(self):
+        for o in (self.out_l, self.out_r):
+            if o.data != self.api.ffi.NULL:
+                self.api.lib.gdf_column_free(o)
+
+    def step(self):
+        self.call()
+        self.free()
+
+    def algorithmic_bytes(self):  # (12 B + 2 bits) per input row + 8 B per output pair
+        return (12 * (self.NL + self.NR) + (self.NL + self.NR) // 4) + 8 * self.pairs
+
+    def check(self):
+        """every left row appears; null left rows exactly once and with -1; matched pairs join equal valid keys."""
+        self.call()
+        n = self.pairs
+        gl = alias(self.api.ffi, self.out_l.data, n, np.int32)
+        gr = alias(self.api.ffi, self.out_r.data, n, np.int32)
+        seen = torch.zeros(self.NL, dtype=torch.int32, device="cuda")
+        seen.index_add_(0, gl.long(), torch.ones_like(gl))
+        lvalid = self.lv0 & self.lv1
+        ok = bool((seen >= 1).all()) and bool((seen[~lvalid] == 1).all())
+        matched = gr >= 0
+        ml, mr = gl[matched].long(), gr[matched].long()
+        ok = ok and bool((self.l0[ml] == self.r0[mr]).all()) and bool((self.l1[ml] == self.r1[mr]).all())
+        ok = ok and bool(lvalid[ml].all()) and bool((self.rv0 & self.rv1)[mr].all())
+        unmatched_null = gl[~matched].long()
+        del seen, gl, gr, ml, mr, unmatched_null
+        self.free()
+        return ok
+
+
+def pack_bits(bits):
+    """bool[n] -> Arrow LSB-first bitmask (synthetic-input preparation, not the product path)."""
+    n = bits.numel()
+    pad = (-n) % 8
+    b = torch.cat([bits, torch.zeros(pad, dtype=torch.bool, device=bits.device)]).view(-1, 8).to(torch.uint8)
+    w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=bits.device)
+    return (b * w).sum(1).to(torch.uint8)
+
+
 def run_workload(api, wl, args, peak_gbs, clocks):
     api.profile_begin()
     ms, (t0, t1) = timed_steps(wl.step, args.warmup, args.steps)
@@ -475,6 +634,22 @@ def kernel_bytes(name, wl):
     if isinstance(wl, FilterWorkload):
         if name == "select":
             return 8 * wl.N + 8 * wl.selected
+    if isinstance(wl, StencilWorkload):
+        if name == "select":
+            return 1 * wl.N + wl.N // 8 + 16 * wl.selected   # stencil bytes + mask in, selected values gathered and written
+        if name == "compare_static":
+            return 8 * wl.N + wl.N + wl.N // 8               # column in, int8 stencil + its mask out
+    if isinstance(wl, ReduceWorkload):
+        if name == "reduce":
+            return wl.algorithmic_bytes()
+    if isinstance(wl, C5Workload):
+        n = wl.NL + wl.NR
+        if name == "join_part_probe":
+            return 16 * wl.NL + 8 * wl.pairs                 # {key 8, tag 4, key2 4} pairs in, index pairs out
+        if name == "join_part_scatter":
+            return (12 + 16) * n / 2.0 + n / 8.0             # two launches: keys + masks in, 16-byte {key,tag,key2} out
+        if name == "join_part_count":
+            return 16 * wl.NL
     return None
 
 
@@ -630,6 +805,118 @@ def bench_dist(args, rank, world, local_rank):
         e2e = {"value": (P + B) / (e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": 8 * (P + B),
                "d2h_bytes_per_step": 8 * pairs, "ms_per_step": e_ms, "steps": e_steps,
                "note": "bytes are the whole job's (all ranks); each rank copies its own shard"}
+    # ---- the other sharded configs of BASELINE.json under the same launch: C4 group-by-sum and C5 left join ----
+    del probe, build
+    torch.cuda.empty_cache()
+    workloads = {}
+    short_steps, short_warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+
+    def run_sharded(step_fn, steps, warm):
+        tm = {}
+
+        def one():
+            r = step_fn(tm)
+            del r
+        for _ in range(warm):
+            one()
+        tm.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return all_max(e0.elapsed_time(e1) / steps), {k: v / steps for k, v in D.resolve_timings(tm).items()}
+
+    if not args.only or "groupby" in args.only:
+        try:
+            N4, G4 = int(1e9 * args.scale), max(int(1e6 * args.scale), 16)
+            lo4, hi4 = D.shard_bounds(N4, world, rank)
+            ranks_ = torch.arange(1, G4 + 1, device="cuda", dtype=torch.float64)
+            cdf = torch.cumsum(ranks_.pow(-1.05), 0)
+            cdf /= cdf[-1].clone()
+            ids = torch.randperm(G4, generator=gen(3), device="cuda", dtype=torch.int64) * 7919 + 13   # same on every rank
+            keys = torch.empty(hi4 - lo4, dtype=torch.int64, device="cuda")
+            g4 = gen(2 + 1000 * rank)
+            for a in range(0, hi4 - lo4, 1 << 27):
+                b = min(hi4 - lo4, a + (1 << 27))
+                u = torch.rand(b - a, generator=g4, device="cuda", dtype=torch.float64)
+                keys[a:b] = ids[torch.searchsorted(cdf, u).clamp_(max=G4 - 1)]
+                del u
+            vals = torch.randint(0, 1000, (hi4 - lo4,), generator=gen(4 + 1000 * rank), device="cuda", dtype=torch.int64)
+            gk, gv = D.distributed_group_by_sum(keys, vals, ops)
+            # parity at full size: sum of sums = sum of values; every key on exactly one rank; #groups = #distinct keys
+            tot_ok = all_sum(int(gv.sum().item())) == all_sum(int(vals.sum().item()))
+            mine = torch.zeros(G4, dtype=torch.int32, device="cuda")
+            pos = torch.searchsorted(torch.sort(ids).values, gk)
+            mine.index_add_(0, pos, torch.ones_like(pos, dtype=torch.int32))
+            dist.all_reduce(mine)
+            present = torch.zeros(G4, dtype=torch.int32, device="cuda")
+            present.index_fill_(0, torch.searchsorted(torch.sort(ids).values, torch.unique(keys)), 1)
+            dist.all_reduce(present, op=dist.ReduceOp.MAX)
+            owner_ok = bool((mine == present).all())
+            groups = all_sum(gk.numel())
+            del gk, gv, mine, present, pos
+            ms4, ph4 = run_sharded(lambda tm: D.distributed_group_by_sum(keys, vals, ops, timings=tm), args.steps, args.warmup)
+            workloads["groupby"] = {"workload": GroupbyWorkload.name + ", rows block-distributed over %d ranks" % world,
+                                    "ms_per_step": ms4, "rows_per_step": N4, "rows_per_s": N4 / (ms4 * 1e-3), "groups": groups,
+                                    "parity_properties_ok": bool(tot_ok and owner_ok), "phases_ms_rank0": ph4,
+                                    "steps": args.steps, "warmup": args.warmup,
+                                    "exchange": "local gdf_group_by_sum, gdf_hash_partition of the partials, one NCCL all_to_all per "
+                                                "column (<= 16 MB per rank), merging gdf_group_by_sum"}
+            del keys, vals
+        except Exception as exc:
+            workloads["groupby"] = {"error": str(exc)[:300]}
+        torch.cuda.empty_cache()
+    if not args.only or "c5" in args.only:
+        try:
+            NL, NR = int(5e8 * args.scale), int(5e7 * args.scale)
+            llo, lhi = D.shard_bounds(NL, world, rank)
+            rlo, rhi = D.shard_bounds(NR, world, rank)
+
+            def side(n, seed):
+                g = gen(seed)
+                k0 = torch.randint(0, NR, (n,), generator=g, device="cuda", dtype=torch.int64)
+                k1 = torch.randint(0, 4, (n,), generator=g, device="cuda", dtype=torch.int32)
+                null_row = torch.rand(n, generator=g, device="cuda") < 0.3
+                which = torch.rand(n, generator=g, device="cuda") < 0.5
+                return k0, k1, ~(null_row & which), ~(null_row & ~which)
+            l0, l1, lv0, lv1 = side(lhi - llo, 100 + rank)
+            r0, r1, rv0, rv1 = side(rhi - rlo, 200 + rank)
+            lmask, rmask = [pack_bits(lv0), pack_bits(lv1)], [pack_bits(rv0), pack_bits(rv1)]
+            gl, gr = D.distributed_left_join_masked([l0, l1], lmask, [r0, r1], rmask, llo, rlo, ops, peer=peer)
+            seen = torch.zeros(NL, dtype=torch.int32, device="cuda")
+            seen.index_add_(0, gl.long(), torch.ones_like(gl))
+            dist.all_reduce(seen)
+            lvalid = lv0 & lv1
+            ok5 = bool((seen[llo:lhi] >= 1).all()) and bool((seen[llo:lhi][~lvalid] == 1).all())
+            del seen
+
+            def gathered(x, total):
+                full = torch.empty(total, dtype=x.dtype, device="cuda")
+                dist.all_gather([full[a:b] for a, b in (D.shard_bounds(total, world, k) for k in range(world))], x)
+                return full
+            L0, L1, LV = gathered(l0, NL), gathered(l1, NL), gathered(lvalid, NL)
+            R0, R1, RV = gathered(r0, NR), gathered(r1, NR), gathered(rv0 & rv1, NR)
+            m = gr >= 0
+            ml, mr = gl[m].long(), gr[m].long()
+            ok5 = ok5 and bool((L0[ml] == R0[mr]).all()) and bool((L1[ml] == R1[mr]).all()) and bool(LV[ml].all()) and bool(RV[mr].all())
+            pairs5 = all_sum(gl.numel())
+            ok5 = all_sum(int(ok5)) == world
+            del L0, L1, LV, R0, R1, RV, gl, gr, ml, mr, m
+            torch.cuda.empty_cache()
+            ms5, ph5 = run_sharded(lambda tm: D.distributed_left_join_masked([l0, l1], lmask, [r0, r1], rmask, llo, rlo, ops,
+                                                                            timings=tm, peer=peer), short_steps, short_warm)
+            workloads["c5"] = {"workload": C5Workload.name + ", rows block-distributed over %d ranks" % world, "ms_per_step": ms5,
+                               "rows_per_step": NL + NR, "rows_per_s": (NL + NR) / (ms5 * 1e-3), "output_pairs": pairs5,
+                               "parity_properties_ok": ok5, "phases_ms_rank0": ph5, "steps": short_steps, "warmup": short_warm}
+            del l0, l1, r0, r1
+        except Exception as exc:
+            workloads["c5"] = {"error": str(exc)[:300]}
+        torch.cuda.empty_cache()
     clocks.stop()
     if rank == 0:
         top = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
@@ -660,6 +947,7 @@ def bench_dist(args, rank, world, local_rank):
                                        % (12 * (P + B) / world * (world - 1) / world / 1e9)}
         if e2e:
             out["e2e"] = e2e
+        out["workloads"] = workloads
         emit(out)
     if peer:
         peer.close()
@@ -832,6 +1120,27 @@ def main():
         except Exception as exc:
             workloads["filter"] = {"error": str(exc)[:300]}
         torch.cuda.empty_cache()
+    # ---- more rows of SURVEY 8a / 8d, each with its own roofline (b200 arm only) ----
+    if args.impl == "b200":
+        extra = [("filter_stencil", lambda: StencilWorkload(api, args.scale), lambda wl: {"selected": wl.selected}),
+                 ("reduce_sum", lambda: ReduceWorkload(api, args.scale, False), lambda wl: {}),
+                 ("reduce_sum_masked", lambda: ReduceWorkload(api, args.scale, True), lambda wl: {}),
+                 ("c5", lambda: C5Workload(api, args.scale), lambda wl: {"output_pairs": wl.pairs})]
+        for key, make, more in extra:
+            if only and key not in only:
+                continue
+            try:
+                wl = make()
+                ok = wl.check()
+                res = run_workload(api, wl, args, peak_gbs, clocks)
+                res["parity_properties_ok"] = ok
+                res.update(more(wl))
+                res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale)
+                workloads[key] = res
+                del wl
+            except Exception as exc:
+                workloads[key] = {"error": str(exc)[:300]}
+            torch.cuda.empty_cache()
     clocks.stop()
 
     out["workloads"] = workloads

@@ -56,6 +56,23 @@ gdf_error gdfx_peer_open(const char *handle64, void **ptr);
 gdf_error gdfx_peer_close(void *ptr);
 gdf_error gdfx_peer_free(void *ptr);
 
+/* Fused partition + exchange, second generation: ONE partition pass per side (PeerExchange.fused_inner_join).
+ * The sender partitions with a COMBINED geometry - bin = destination rank * nlocal + the receiver's local radix
+ * partition (nlocal a power of two, ranks * nlocal <= 256) - and stores compact {key32, id32} pairs straight into the
+ * destination's pair buffer, so what a rank receives is already partition-contiguous and it joins it without a
+ * histogram / scatter pass of its own.  Applies when every build key fits 32 bits (hi_or == 0 on all ranks).
+ *   gdfx_xjoin_count    counts[r * nlocal + p] (host) = rows of `key` going to (rank r, local partition p);
+ *                       *hi_or = OR of the keys' high words
+ *   gdfx_xjoin_scatter  dst_pairs[r] = rank r's pair buffer as mapped on this device (gdfx_peer_open), 8 bytes per
+ *                       pair; dst_offsets[r * nlocal + p] (host) = where this rank's pairs of that bin start
+ *   gdfx_xjoin_local    INNER join of this rank's received pairs; *_counts[p] (host) = pairs of local partition p
+ *                       (summed over the senders); outputs hold the travelling ids, as gdfx_join_pairs */
+gdf_error gdfx_xjoin_count(gdf_column *key, int ranks, int nlocal, unsigned long long *counts, unsigned *hi_or);
+gdf_error gdfx_xjoin_scatter(gdf_column *key, int32_t id_base, int ranks, int nlocal, void * const *dst_pairs,
+                             const unsigned long long *dst_offsets);
+gdf_error gdfx_xjoin_local(const void *probe_pairs, const unsigned long long *probe_counts, const void *build_pairs,
+                           const unsigned long long *build_counts, int nlocal, gdf_column *out_l, gdf_column *out_r);
+
 /* Multi-GPU layer, composite-key joins with NULLs (C5): row validity travels with the rows as a byte
  * column.  gdfx_rows_valid_to_bytes: out[i] = 1 iff every column's validity bit i is set (no mask = all
  * valid; the reference's row-valid rule, gdf_table.cuh:63-98).  gdfx_bytes_to_valid: LSB-first Arrow bitmask

@@ -18,6 +18,7 @@
 //   apply_stencil       streamcompactionops.cu:208-339   see DESIGN.md "quirks" for the two
 //                       documented divergences (LESS_THAN operators, rebuilt output mask).
 #include "select.cuh"
+#include "select_chunked.cuh"
 #include "select_stream.cuh"
 
 namespace b200 {
@@ -178,16 +179,17 @@ gdf_error run_filter_stream(const T* data, size_t n, const void* const* d_vals, 
   using G = select_stream::Geom<T>;
   const size_t chunks = (n + G::kChunkRows - 1) / G::kChunkRows;
   B200_REQUIRE(chunks < (1ull << 31), GDF_COLUMN_SIZE_TOO_BIG);
-  Scratch desc;  // [chunks] look-back descriptors | selected count
-  const size_t bytes = chunks * sizeof(uint64_t) + sizeof(unsigned long long);
+  Scratch desc;  // [chunks] look-back descriptors | selected count | chunk ticket
+  const size_t bytes = chunks * sizeof(uint64_t) + 2 * sizeof(unsigned long long);
   B200_CUDA_TRY(desc.alloc(bytes));
   B200_CUDA_TRY(cudaMemsetAsync(desc.ptr, 0, bytes, 0));
   uint64_t* d = desc.as<uint64_t>();
   unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + chunks);
+  unsigned* d_ticket = reinterpret_cast<unsigned*>(d_count + 1);
   auto kern = select_stream::select_stream_kernel<T, EqualsDeviceScalar<T>, EmitRowIndex>;
   const int smem = (int)select_stream::smem_bytes<T>();
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  int per_sm = 0;  // the look-back needs every CTA of the grid to be co-resident
+  int per_sm = 0;  // persistent CTAs: one resident wave (chunk tickets keep the look-back live even if fewer run)
   B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, select_stream::kThreads, smem));
   B200_REQUIRE(per_sm >= 1, GDF_CUDA_ERROR);
   const size_t resident = (size_t)sm_count() * (size_t)per_sm;
@@ -195,37 +197,40 @@ gdf_error run_filter_stream(const T* data, size_t n, const void* const* d_vals, 
   {
     B200_TIMED("select");
     kern<<<blocks, select_stream::kThreads, smem>>>(data, n, EqualsDeviceScalar<T>{d_vals, T()}, EmitRowIndex{out}, d,
-                                                    d_count);
+                                                    d_count, d_ticket);
   }
   B200_CHECK_LAST();
   return read_count(d_count, h_count);
 }
 
-// Launch one select pass; returns the number of selected rows through *h_count (host).
+// Launch one select pass (select_chunked.cuh); returns the number of selected rows through *h_count (host).
 template <typename Policy>
 gdf_error run_select(const Policy& pol, size_t n, size_t* h_count) {
   if (n == 0) {
     *h_count = 0;
     return GDF_SUCCESS;
   }
-  const size_t tiles = select_tiles<Policy>(n);
-  B200_REQUIRE(tiles < (1ull << 31), GDF_COLUMN_SIZE_TOO_BIG);
-  Scratch desc;
-  B200_CUDA_TRY(desc.alloc(tiles * sizeof(uint64_t) + sizeof(unsigned long long)));
-  B200_CUDA_TRY(cudaMemsetAsync(desc.ptr, 0, tiles * sizeof(uint64_t) + sizeof(unsigned long long), 0));
+  using G = select_chunked::Geom<Policy>;
+  const size_t chunks = (n + G::kChunkRows - 1) / G::kChunkRows;
+  B200_REQUIRE(chunks < (1ull << 31), GDF_COLUMN_SIZE_TOO_BIG);
+  Scratch desc;  // [chunks] look-back descriptors | selected count | chunk ticket
+  const size_t bytes = chunks * sizeof(uint64_t) + 2 * sizeof(unsigned long long);
+  B200_CUDA_TRY(desc.alloc(bytes));
+  B200_CUDA_TRY(cudaMemsetAsync(desc.ptr, 0, bytes, 0));
   uint64_t* d = desc.as<uint64_t>();
-  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + tiles);
+  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + chunks);
+  unsigned* d_ticket = reinterpret_cast<unsigned*>(d_count + 1);
+  auto kern = select_chunked::select_chunked_kernel<Policy>;
+  int per_sm = 0;
+  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, select_chunked::kThreads, 0));
+  const size_t resident = (size_t)sm_count() * (size_t)(per_sm > 0 ? per_sm : 1);
+  const unsigned blocks = (unsigned)(chunks < resident ? chunks : resident);
   {
     B200_TIMED("select");
-    select_kernel<Policy><<<(unsigned)tiles, select_detail::kThreads>>>(pol, n, d, d_count);
+    kern<<<blocks, select_chunked::kThreads>>>(pol, n, d, d_count, d_ticket);
   }
   B200_CHECK_LAST();
-  unsigned long long* box = static_cast<unsigned long long*>(pinned_mailbox());
-  B200_REQUIRE(box != nullptr, GDF_CUDA_ERROR);
-  B200_CUDA_TRY(cudaMemcpyAsync(box, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, 0));
-  B200_CUDA_TRY(cudaStreamSynchronize(0));
-  *h_count = (size_t)*box;
-  return GDF_SUCCESS;
+  return read_count(d_count, h_count);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -169,6 +169,7 @@ gdf_error run_partition(const TableView& keys, const ColumnMove& mv, int num_par
   size_t want = (rows + kTileRows - 1) / kTileRows;
   const size_t cap = (size_t)sm_count() * 4;
   const int blocks = (int)(want < cap ? (want ? want : 1) : cap);
+  B200_TIMED("hash_partition");
   if (smem)
     partition_hist_kernel<IDENTITY, true><<<blocks, kThreads, P * sizeof(unsigned)>>>(keys, part, totals);
   else

@@ -45,6 +45,11 @@ gdf_error partition_pairs(const gdf_column* key, int32_t id_base, unsigned num_p
 gdf_error partition_count(const gdf_column* key, unsigned num_partitions, unsigned long long* h_counts);
 gdf_error partition_scatter_peer(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* const* dst_keys,
                                  int32_t* const* dst_ids, const unsigned long long* dst_offsets);
+gdf_error xjoin_count(const gdf_column* key, unsigned ranks, unsigned nlocal, unsigned long long* h_counts, unsigned* hi_or);
+gdf_error xjoin_scatter(const gdf_column* key, int32_t id_base, unsigned ranks, unsigned nlocal, void* const* dst_pairs,
+                        const unsigned long long* h_offsets);
+gdf_error xjoin_local(const void* probe_pairs, const unsigned long long* probe_counts, const void* build_pairs,
+                      const unsigned long long* build_counts, unsigned nlocal, gdf_column* out_l, gdf_column* out_r);
 
 namespace {
 
@@ -466,6 +471,7 @@ gdf_error gather_columns(gdf_column* const* in_cols, gdf_column* const* out_cols
                          const gdf_column* indices, bool merge_valid) {
   const size_t n = indices->size;
   if (n == 0 || ncols == 0) return GDF_SUCCESS;
+  B200_TIMED("join_gather");
   for (int base = 0; base < ncols; base += kMaxCols) {
     GatherCols g;
     g.ncols = ncols - base < kMaxCols ? ncols - base : kMaxCols;
@@ -687,6 +693,34 @@ extern "C" gdf_error gdfx_partition_scatter_peer(gdf_column* key, int32_t id_bas
   B200_REQUIRE(key->size < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
   if (key->size == 0) return GDF_SUCCESS;
   return partition_scatter_peer(key, id_base, (unsigned)num_partitions, dst_keys, dst_ids, dst_offsets);
+}
+
+// ---- fused exchange, one partition pass per side (include/gdf_b200_ext.h) ----
+extern "C" gdf_error gdfx_xjoin_count(gdf_column* key, int ranks, int nlocal, unsigned long long* counts, unsigned* hi_or) {
+  B200_REQUIRE(key != nullptr && counts != nullptr && hi_or != nullptr, GDF_DATASET_EMPTY);
+  B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
+  B200_REQUIRE(ranks >= 1 && nlocal >= 1, GDF_INVALID_API_CALL);
+  *hi_or = 0;
+  if (key->size == 0) {
+    for (int p = 0; p < ranks * nlocal; ++p) counts[p] = 0;
+    return GDF_SUCCESS;
+  }
+  return xjoin_count(key, (unsigned)ranks, (unsigned)nlocal, counts, hi_or);
+}
+extern "C" gdf_error gdfx_xjoin_scatter(gdf_column* key, int32_t id_base, int ranks, int nlocal, void* const* dst_pairs,
+                                        const unsigned long long* dst_offsets) {
+  B200_REQUIRE(key && dst_pairs && dst_offsets, GDF_DATASET_EMPTY);
+  B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
+  B200_REQUIRE(key->size < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
+  B200_REQUIRE(ranks >= 1 && nlocal >= 1, GDF_INVALID_API_CALL);
+  if (key->size == 0) return GDF_SUCCESS;
+  return xjoin_scatter(key, id_base, (unsigned)ranks, (unsigned)nlocal, dst_pairs, dst_offsets);
+}
+extern "C" gdf_error gdfx_xjoin_local(const void* probe_pairs, const unsigned long long* probe_counts, const void* build_pairs,
+                                      const unsigned long long* build_counts, int nlocal, gdf_column* out_l, gdf_column* out_r) {
+  B200_REQUIRE(probe_pairs && probe_counts && build_pairs && build_counts && out_l && out_r, GDF_DATASET_EMPTY);
+  B200_REQUIRE(nlocal >= 1, GDF_INVALID_API_CALL);
+  return xjoin_local(probe_pairs, probe_counts, build_pairs, build_counts, (unsigned)nlocal, out_l, out_r);
 }
 
 // Receive buffers that other ranks (processes) can map: plain cudaMalloc + legacy CUDA IPC handle (64 bytes).

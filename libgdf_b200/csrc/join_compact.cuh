@@ -476,9 +476,21 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
   uint2* const ring = ring_all + (size_t)warp * kC32Stages * kC32Tile;
   uint64_t* const bar = sm.bar[warp];
   uint4* const queue = sm.queue[warp];
-  uint64_t pol_stream, pol_table;
+  uint64_t pol_stream, pol_table, pol_store;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_table));
+  pol_store = pol_stream;
+#ifdef B200_LAB   // L2 policy A/B (lab >> 8): bit 0 pairs normal, bit 1 tables normal, bit 2 stores normal, bit 3 stores evict_last
+  {
+    uint64_t pol_normal;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_normal));
+    const unsigned hk = lab >> 8;
+    if (hk & 1u) pol_stream = pol_normal;
+    if (hk & 2u) pol_table = pol_normal;
+    if (hk & 4u) pol_store = pol_normal;
+    if (hk & 8u) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_store));
+  }
+#endif
   for (unsigned p = tid; p < g.nparts; p += kC32Threads) {
     sm.part_off[p] = (unsigned)t.offset[p];
     sm.part_mask[p] = t.mask[p] & ~3u;
@@ -655,13 +667,13 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
         if (((live >> i) & 1u) && !((pend >> i) & 1u)) {
           const size_t j = row0 + i * 32 + lane;
           const int32_t tg = (int32_t)pair_at(i).y;
-          st_i32_stream(out.probe + j, tg >= 0 ? tg : ~tg, pol_stream);
-          st_i32_stream(out.build + j, first[i], pol_stream);
+          st_i32_stream(out.probe + j, tg >= 0 ? tg : ~tg, pol_store);
+          st_i32_stream(out.build + j, first[i], pol_store);
         }
       }
       if (qdone) {
-        st_i32_stream(out.probe + qe.z, (int32_t)qe.y, pol_stream);
-        st_i32_stream(out.build + qe.z, qfirst, pol_stream);
+        st_i32_stream(out.probe + qe.z, (int32_t)qe.y, pol_store);
+        st_i32_stream(out.build + qe.z, qfirst, pol_store);
       }
     } else {
       // ---- INNER: ranks from ballots, positions from the warp's chunk ----
@@ -689,13 +701,13 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
 #pragma unroll
         for (int i = 0; i < kC32Rows; ++i) {
           if (first[i] >= 0) {
-            st_i32_stream(po + rank[i], (int32_t)pair_at(i).y, pol_stream);
-            st_i32_stream(bo + rank[i], first[i], pol_stream);
+            st_i32_stream(po + rank[i], (int32_t)pair_at(i).y, pol_store);
+            st_i32_stream(bo + rank[i], first[i], pol_store);
           }
         }
         if (qdone && qfirst >= 0) {
-          st_i32_stream(po + qrank, (int32_t)qe.y, pol_stream);
-          st_i32_stream(bo + qrank, qfirst, pol_stream);
+          st_i32_stream(po + qrank, (int32_t)qe.y, pol_store);
+          st_i32_stream(bo + qrank, qfirst, pol_store);
         }
       } else {  // split: the first in_old pairs finish the current chunk, the rest start the next one
         const unsigned in_old = kC32Chunk - chunk_used;
@@ -709,13 +721,13 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
         for (int i = 0; i < kC32Rows; ++i) {
           if (first[i] < 0) continue;
           const size_t pos = place(rank[i]);
-          st_i32_stream(out.probe + pos, (int32_t)pair_at(i).y, pol_stream);
-          st_i32_stream(out.build + pos, first[i], pol_stream);
+          st_i32_stream(out.probe + pos, (int32_t)pair_at(i).y, pol_store);
+          st_i32_stream(out.build + pos, first[i], pol_store);
         }
         if (qdone && qfirst >= 0) {
           const size_t pos = place(qrank);
-          st_i32_stream(out.probe + pos, (int32_t)qe.y, pol_stream);
-          st_i32_stream(out.build + pos, qfirst, pol_stream);
+          st_i32_stream(out.probe + pos, (int32_t)qe.y, pol_store);
+          st_i32_stream(out.build + pos, qfirst, pol_store);
         }
       }
     }

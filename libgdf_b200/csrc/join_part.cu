@@ -85,11 +85,15 @@ static __device__ __forceinline__ uint32_t with_k2(uint32_t h, uint32_t k2) {
 static __device__ __forceinline__ uint32_t slot_hash(uint32_t h) { return ((h * 0x9E3779B1u) >> 7) & ~1u; }
 
 struct PartGeom {
-  unsigned nparts;  // power of two (local radix partitions) or any count (dest mode)
-  unsigned shift;   // pid = hash >> shift   (shift = 32 - log2(nparts)); nparts == 1 -> pid = 0
+  unsigned nparts;  // power of two (local radix partitions) or any count (dest modes)
+  unsigned shift;   // local partition = hash >> shift   (shift = 32 - log2(#local partitions)); one partition -> 0
   unsigned dest;    // 1 = "destination rank" mode of the multi-GPU layer: pid = mulhi(remix(hash), nparts), a
-                    // function that is independent of the top bits the receiver's local partitioning uses
+                    //     function that is independent of the top bits the receiver's local partitioning uses
+                    // 2 = combined mode (fused exchange): pid = destination rank * nlocal + the receiver's local
+                    //     partition, so that ONE pass on the sender does the work of both partition passes
+  unsigned nlocal;  // dest == 2: local partitions per destination (power of two); nparts = ranks * nlocal
   __device__ __forceinline__ unsigned pid(uint32_t h) const {
+    if (dest == 2u) return __umulhi(fmix32(h ^ 0x5bd1e995u), nparts / nlocal) * nlocal + (nlocal == 1 ? 0u : (h >> shift));
     if (dest & 1u) return __umulhi(fmix32(h ^ 0x5bd1e995u), nparts);
     return nparts == 1 ? 0u : (h >> shift);
   }
@@ -347,11 +351,20 @@ struct Scatter32Smem {
   unsigned long long gbase[kMaxParts];
 };
 
+// Fused exchange (multi-GPU layer, combined geometry): bin = destination rank * nlocal + local partition, and the
+// bin's run goes straight into THAT rank's pair buffer - peer memory mapped through CUDA IPC, so the stores cross
+// NVLink from inside this kernel and arrive already in the receiver's partition order.
+struct PeerPairs {
+  uint2* base[kMaxPeers];
+  unsigned on;      // 0: everything goes to out_pairs
+  unsigned shift;   // destination rank = bin >> shift  (shift = log2(nlocal))
+};
+
 template <typename KT, bool KEEP_NULLS>
 __global__ void __launch_bounds__(kS32Threads, sizeof(KT) == 8 ? 3 : 4)
 part_scatter32_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restrict__ valid, size_t n, PartGeom g,
                       unsigned long long* __restrict__ cursors, uint2* __restrict__ out_pairs,
-                      const int32_t* __restrict__ payload, int32_t id_base) {
+                      const int32_t* __restrict__ payload, int32_t id_base, const PeerPairs peer) {
   extern __shared__ __align__(16) unsigned char scatter32_smem[];
   Scatter32Smem& sm = *reinterpret_cast<Scatter32Smem*>(scatter32_smem);
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -429,7 +442,8 @@ part_scatter32_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restr
     const unsigned kept = sm.lstart[g.nparts - 1] + sm.hist[buf][g.nparts - 1];
     for (unsigned j = threadIdx.x; j < kept; j += kS32Threads) {
       const unsigned p = sm.pid[j];
-      out_pairs[sm.gbase[p] + (j - sm.lstart[p])] = sm.pairs[j];
+      uint2* const dst = peer.on ? peer.base[p >> peer.shift] : out_pairs;
+      dst[sm.gbase[p] + (j - sm.lstart[p])] = sm.pairs[j];
     }
   }
 }
@@ -1103,7 +1117,13 @@ gdf_error partition_hist(const gdf_column* col, PartGeom g, unsigned long long* 
 
 template <typename KT, bool KEEP_NULLS>
 gdf_error partition_scatter32(const gdf_column* col, PartGeom g, const unsigned long long* h_cursors,
-                              unsigned long long* d_cursors, uint2* out_pairs, const int32_t* payload, int32_t id_base) {
+                              unsigned long long* d_cursors, uint2* out_pairs, const int32_t* payload, int32_t id_base,
+                              const PeerPairs* peer_dst = nullptr) {
+  PeerPairs peer;
+  peer.on = 0;
+  peer.shift = 0;
+  for (int r = 0; r < kMaxPeers; ++r) peer.base[r] = nullptr;
+  if (peer_dst) peer = *peer_dst;
   const KT* keys = static_cast<const KT*>(col->data);
   const size_t n = col->size;
   B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
@@ -1117,7 +1137,7 @@ gdf_error partition_scatter32(const gdf_column* col, PartGeom g, const unsigned 
   const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
   {
     B200_TIMED("join_part_scatter");
-    kern<<<sblocks, kS32Threads, smem_bytes>>>(keys, col->valid, n, g, d_cursors, out_pairs, payload, id_base);
+    kern<<<sblocks, kS32Threads, smem_bytes>>>(keys, col->valid, n, g, d_cursors, out_pairs, payload, id_base, peer);
   }
   B200_CHECK_LAST();
   return GDF_SUCCESS;
@@ -1284,12 +1304,13 @@ gdf_error run_compact(int kind, bool flip, PartGeom g, const Pairs32& bp, const 
   B200_CUDA_TRY(table.alloc(total_slots * sizeof(unsigned long long)));
   Tables32 t{table.as<unsigned long long>(), d_toffset, d_tmask};
   {
-    // Tables are initialised and filled a few partitions at a time (<= 48 MB of slots per round): the EMPTY pattern
-    // written by the memset is still in L2 when the inserts arrive, so a bucket fetch is an L2 hit instead of a random
-    // 32-byte DRAM read (ncu, one memset + one build launch: 2.9 GB read + 1.6 GB written by the build kernel, 2.85 ms,
-    // latency-bound on those misses), and every table sector goes to DRAM once instead of twice.
+    // Tables can be initialised and filled a few partitions at a time (lab knob B200_BUILD_ROUND_MB) so that the EMPTY
+    // pattern written by the memset is still in L2 when the inserts arrive (ncu, one memset + one build launch: 2.9 GB
+    // read + 1.6 GB written by the build kernel, 2.85 ms).
     B200_TIMED("join_part_build");
-    constexpr unsigned long long kRoundSlots = (48ull << 20) / sizeof(unsigned long long);
+    // measured (profiles/r02_notes.md): 32 rounds of 48 MB cost 3.70 ms against 3.17 ms for ONE memset + ONE build launch -
+    // the launch gaps and tails of 64 small launches outweigh the L2 hits - so the default is a single round
+    const unsigned long long kRoundSlots = ((unsigned long long)lab_knob("B200_BUILD_ROUND_MB", 1 << 20) << 20) / sizeof(unsigned long long);
     unsigned long long pair_lo = 0;
     for (unsigned p = 0; p < g.nparts;) {
       unsigned q = p;
@@ -1425,6 +1446,7 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   const bool left_like = kind != JOIN_INNER;
   PartGeom g;
   g.dest = 0;
+  g.nlocal = 0;
   {
     unsigned np = pow2_at_least((B + kRowsPerPartition - 1) / kRowsPerPartition);
     if (np > kMaxParts) np = kMaxParts;
@@ -1634,6 +1656,7 @@ gdf_error partition_pairs_typed(const gdf_column* key, int32_t id_base, unsigned
   g.nparts = num_partitions;
   g.shift = 0;
   g.dest = 1;
+  g.nlocal = 0;
   Scratch small, unused_a, unused_b;
   B200_CUDA_TRY(small.alloc((2 * (size_t)num_partitions + 1) * sizeof(unsigned long long)));
   unsigned long long h_tot[kMaxParts];
@@ -1658,6 +1681,7 @@ gdf_error partition_count(const gdf_column* key, unsigned num_partitions, unsign
   g.nparts = num_partitions;
   g.shift = 0;
   g.dest = 1;
+  g.nlocal = 0;
   Scratch small;
   B200_CUDA_TRY(small.alloc(((size_t)num_partitions + 1) * sizeof(unsigned long long)));
   switch (key->dtype) {
@@ -1677,6 +1701,7 @@ gdf_error partition_scatter_peer(const gdf_column* key, int32_t id_base, unsigne
   g.nparts = num_partitions;
   g.shift = 0;
   g.dest = 1;
+  g.nlocal = 0;
   PeerDst peer;
   peer.on = 1;
   for (int p = 0; p < kMaxPeers; ++p) {
@@ -1694,6 +1719,100 @@ gdf_error partition_scatter_peer(const gdf_column* key, int32_t id_base, unsigne
                                                 nullptr, id_base, peer);
     default: return GDF_UNSUPPORTED_DTYPE;
   }
+}
+
+// ---- fused exchange, second generation (multi-GPU layer): ONE partition pass per side ----
+// The sender's histogram / scatter use the COMBINED geometry (destination rank x the receiver's local partition), so
+// the pairs arrive in the receiver's buffers already partition-contiguous and in the compact {key32, tag32} form;
+// the receiver goes straight to table build + probe (run_compact) without a histogram or scatter of its own.
+// Round 1 scattered every row twice (by destination over NVLink, then again locally): 4.2 of 7.8 ms at 8 GPUs.
+PartGeom combined_geom(unsigned ranks, unsigned nlocal) {
+  PartGeom g;
+  g.nparts = ranks * nlocal;
+  g.dest = 2;
+  g.nlocal = nlocal;
+  unsigned lg = 0;
+  while ((1u << lg) < nlocal) ++lg;
+  g.shift = 32 - lg;
+  return g;
+}
+
+// counts[ranks * nlocal] (host) = rows of `key` per (destination, local partition); *hi_or = OR of the high words of
+// the keys (0 for 4-byte keys): the compact exchange applies when it is 0 on the build side of every rank.
+gdf_error xjoin_count(const gdf_column* key, unsigned ranks, unsigned nlocal, unsigned long long* h_counts, unsigned* hi_or) {
+  B200_REQUIRE(ranks >= 1 && ranks <= (unsigned)kMaxPeers && nlocal >= 1 && (nlocal & (nlocal - 1)) == 0 &&
+                   ranks * nlocal <= kMaxParts, GDF_INVALID_API_CALL);
+  const PartGeom g = combined_geom(ranks, nlocal);
+  Scratch small;
+  B200_CUDA_TRY(small.alloc(((size_t)g.nparts + 1) * sizeof(unsigned long long)));
+  switch (key->dtype) {
+    case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
+      return partition_hist<uint64_t, false, true>(key, g, small.as<unsigned long long>(), h_counts, nullptr, hi_or);
+    case GDF_INT32: case GDF_DATE32:
+      return partition_hist<uint32_t, false, true>(key, g, small.as<unsigned long long>(), h_counts, nullptr, hi_or);
+    default: return GDF_UNSUPPORTED_DTYPE;
+  }
+}
+
+// dst_pairs[r] = rank r's pair buffer as mapped on THIS device; h_offsets[r * nlocal + p] = position inside it of this
+// rank's first pair of local partition p.  Rows whose key does not fit 32 bits are dropped (they cannot match).
+gdf_error xjoin_scatter(const gdf_column* key, int32_t id_base, unsigned ranks, unsigned nlocal, void* const* dst_pairs,
+                        const unsigned long long* h_offsets) {
+  B200_REQUIRE(ranks >= 1 && ranks <= (unsigned)kMaxPeers && nlocal >= 1 && (nlocal & (nlocal - 1)) == 0 &&
+                   ranks * nlocal <= kMaxParts, GDF_INVALID_API_CALL);
+  const PartGeom g = combined_geom(ranks, nlocal);
+  PeerPairs peer;
+  peer.on = 1;
+  peer.shift = 32 - g.shift;
+  for (int r = 0; r < kMaxPeers; ++r) peer.base[r] = r < (int)ranks ? static_cast<uint2*>(dst_pairs[r]) : nullptr;
+  Scratch small;
+  B200_CUDA_TRY(small.alloc((size_t)g.nparts * sizeof(unsigned long long)));
+  switch (key->dtype) {
+    case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
+      return partition_scatter32<uint64_t, false>(key, g, h_offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer);
+    case GDF_INT32: case GDF_DATE32:
+      return partition_scatter32<uint32_t, false>(key, g, h_offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer);
+    default: return GDF_UNSUPPORTED_DTYPE;
+  }
+}
+
+// INNER join of partition-contiguous compact pairs (this rank's receive buffers): counts[p] = pairs of local partition p.
+gdf_error xjoin_local(const void* probe_pairs, const unsigned long long* probe_counts, const void* build_pairs,
+                      const unsigned long long* build_counts, unsigned nlocal, gdf_column* out_l, gdf_column* out_r) {
+  B200_REQUIRE(nlocal >= 1 && nlocal <= kMaxParts && (nlocal & (nlocal - 1)) == 0, GDF_INVALID_API_CALL);
+  PartGeom g;
+  g.nparts = nlocal;
+  g.dest = 0;
+  g.nlocal = 0;
+  unsigned lg = 0;
+  while ((1u << lg) < nlocal) ++lg;
+  g.shift = 32 - lg;
+  unsigned long long h_pstart[kMaxParts + 1], build_rows = 0, probe_rows = 0, slots32 = 0;
+  for (unsigned p = 0; p < nlocal; ++p) {
+    h_pstart[p] = probe_rows;
+    probe_rows += probe_counts[p];
+    build_rows += build_counts[p];
+    B200_REQUIRE(build_counts[p] <= (1u << 22), GDF_COLUMN_SIZE_TOO_BIG);  // limits of the compact probe (run_partitioned)
+    slots32 += pow2_at_least(build_counts[p] ? 2 * build_counts[p] : 4);
+  }
+  h_pstart[nlocal] = probe_rows;
+  B200_REQUIRE(slots32 < (1ull << 32) - 8, GDF_COLUMN_SIZE_TOO_BIG);
+  view_indices(out_l, nullptr, 0);
+  view_indices(out_r, nullptr, 0);
+  if (probe_rows == 0 || build_rows == 0) return GDF_SUCCESS;
+  Scratch small;  // toffset[np] | cursor, flags (64 bytes) | pstart[np + 1] | tmask[np]
+  B200_CUDA_TRY(small.alloc(((size_t)nlocal * 2 + 1) * sizeof(unsigned long long) + 64 + nlocal * sizeof(unsigned)));
+  unsigned long long* d_toffset = small.as<unsigned long long>();
+  unsigned long long* d_cursor = d_toffset + nlocal;
+  int* d_flags = reinterpret_cast<int*>(d_cursor + 1);
+  unsigned long long* d_pstart = d_cursor + 8;
+  unsigned* d_tmask = reinterpret_cast<unsigned*>(d_pstart + nlocal + 1);
+  B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 64, 0));
+  B200_CUDA_TRY(cudaMemcpy(d_pstart, h_pstart, (nlocal + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  const Pairs32 bp{static_cast<const uint2*>(build_pairs), (size_t)build_rows};
+  const Pairs32 pp{static_cast<const uint2*>(probe_pairs), (size_t)probe_rows};
+  return run_compact(JOIN_INNER, false, g, bp, pp, build_counts, (size_t)build_rows, d_toffset, d_tmask, d_cursor, d_flags,
+                     d_pstart, out_l, out_r);
 }
 
 gdf_error partition_pairs(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* out_keys,

@@ -43,6 +43,7 @@ struct Smem {
   uint64_t bar[kStages];
   uint32_t warp_tot[kChunkTiles][kWarps];
   uint64_t chunk_excl;
+  unsigned chunk_ids[2];   // tickets of this CTA's current and next chunk (index: CTA-local chunk number & 1)
 };
 
 template <typename T>
@@ -97,12 +98,15 @@ static __device__ __forceinline__ uint64_t lookback_wide(uint64_t* desc, unsigne
 
 // Pred: void prepare() (once per thread, may read device scalars); bool operator()(T) const.
 // Emit: void operator()(size_t row, size_t pos) const.
-// Chunks are dealt round-robin (CTA b: chunks b, b + grid, ...); the grid never exceeds what is
-// co-resident (occupancy API on the host), so the CTA holding a predecessor chunk is always running.
+// Chunks are taken through an atomic TICKET, one chunk ahead of the one being processed (the ring prefetches
+// across the chunk boundary).  Tickets are handed out in increasing order to CTAs that are already running, so
+// every predecessor of a chunk is held by a running CTA: the look-back always makes progress, whether or not the
+// whole grid is co-resident (another stream's persistent kernel may hold SMs).  Round 1 dealt chunks statically
+// (CTA b: b, b + grid, ...), which was only safe with the full grid resident.
 template <typename T, typename Pred, typename Emit>
 __global__ void __launch_bounds__(kThreads)
 select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit, uint64_t* __restrict__ desc,
-                     unsigned long long* __restrict__ count_out) {
+                     unsigned long long* __restrict__ count_out, unsigned* __restrict__ ticket) {
   using G = Geom<T>;
   extern __shared__ __align__(16) unsigned char select_smem[];
   unsigned char* const ring = select_smem;
@@ -112,10 +116,10 @@ select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit,
   const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
   pred.prepare();
 
-  // The CTA's tiles form one sequence q = 0, 1, 2, ...: tile q is tile (q % 16) of chunk
-  // blockIdx.x + (q / 16) * gridDim.x and lives in ring stage q % kStages.
+  // The CTA's tiles form one sequence q = 0, 1, 2, ...: tile q is tile (q % 16) of the CTA's (q / 16)-th chunk and
+  // lives in ring stage q % kStages.  Only thread 0 calls this (it is the thread that takes the tickets).
   auto tile_index = [&](unsigned q) {
-    return ((size_t)blockIdx.x + (size_t)(q / kChunkTiles) * gridDim.x) * kChunkTiles + (q % kChunkTiles);
+    return (size_t)sm.chunk_ids[(q / kChunkTiles) & 1u] * kChunkTiles + (q % kChunkTiles);
   };
   auto issue = [&](unsigned q) {  // one thread starts the copy of the CTA's q-th tile (full tiles only)
     const size_t t = tile_index(q);
@@ -129,6 +133,7 @@ select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit,
 #pragma unroll
     for (int s = 0; s < kStages; ++s) tma::mbar_init(&sm.bar[s], 1);
     tma::fence_barrier_init();
+    sm.chunk_ids[0] = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int s = 0; s < kStages; ++s) issue((unsigned)s);
   }
@@ -136,7 +141,10 @@ select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit,
 
   unsigned q = 0;                  // tiles consumed so far by this CTA
   unsigned phase_bits = 0;         // bit s = parity the next FULL tile of stage s completes
-  for (size_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+  for (unsigned j = 0;; ++j) {     // j = CTA-local chunk number
+    const size_t chunk = sm.chunk_ids[j & 1u];
+    if (chunk >= chunks) break;
+    if (tid == 0) sm.chunk_ids[(j + 1) & 1u] = atomicAdd(ticket, 1u);  // next chunk: needed by the prefetch from tile 13 on
     uint32_t f[kChunkTiles], excl[kChunkTiles];
 #pragma unroll
     for (int k = 0; k < kChunkTiles; ++k, ++q) {

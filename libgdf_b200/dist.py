@@ -129,6 +129,28 @@ class GdfOps(object):
         off = ffi.new("unsigned long long[]", [int(o) for o in dst_offsets])
         lib.gdfx_partition_scatter_peer(self.C.Column(keys).cdata, id_base, n, kp, ip, off)
 
+    def xjoin_count(self, keys, ranks, nlocal):
+        """Rows of `keys` per (destination rank, receiver-local partition) + OR of the keys' high words."""
+        ffi, lib = self.ffi, self.lib
+        counts = ffi.new("unsigned long long[]", ranks * nlocal)
+        hi = ffi.new("unsigned*")
+        lib.gdfx_xjoin_count(self.C.Column(keys).cdata, ranks, nlocal, counts, hi)
+        return [int(counts[i]) for i in range(ranks * nlocal)], int(hi[0])
+
+    def xjoin_scatter(self, keys, id_base, ranks, nlocal, dst_ptrs, offsets):
+        ffi, lib = self.ffi, self.lib
+        dp = ffi.new("void*[]", [ffi.cast("void*", p) for p in dst_ptrs])
+        off = ffi.new("unsigned long long[]", [int(o) for o in offsets])
+        lib.gdfx_xjoin_scatter(self.C.Column(keys).cdata, id_base, ranks, nlocal, dp, off)
+
+    def xjoin_local(self, probe_ptr, probe_counts, build_ptr, build_counts, nlocal):
+        C, ffi, lib = self.C, self.ffi, self.lib
+        out_l, out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
+        lib.gdfx_xjoin_local(ffi.cast("void*", probe_ptr), ffi.new("unsigned long long[]", [int(c) for c in probe_counts]),
+                             ffi.cast("void*", build_ptr), ffi.new("unsigned long long[]", [int(c) for c in build_counts]),
+                             nlocal, out_l, out_r)
+        return C.library_owned_to_torch(out_l), C.library_owned_to_torch(out_r)
+
     def peer_alloc(self, nbytes):
         ffi, lib = self.ffi, self.lib
         ptr = ffi.new("void**")
@@ -284,14 +306,68 @@ class PeerExchange(object):
         dist.barrier(group=self.group)
         for r in range(self.world):
             if r != self.rank:
-                self.ops.peer_close(slot["peers"][0][r]), self.ops.peer_close(slot["peers"][1][r])
+                for peers in slot["peers"]:
+                    self.ops.peer_close(peers[r])
         dist.barrier(group=self.group)
-        self.ops.peer_free(slot["mine"][0]), self.ops.peer_free(slot["mine"][1])
+        for ptr in slot["mine"]:
+            self.ops.peer_free(ptr)
 
     def close(self):
         for slot in self.slots.values():
             self._release(slot)
         self.slots = {}
+
+    def _ensure_pairs(self, name, rows):
+        """One IPC-shared buffer of 8-byte {key32, id32} pairs per name (fused one-pass exchange)."""
+        slot = self.slots.get(name)
+        if slot and slot["cap"] >= rows and slot.get("pairs"):
+            return slot
+        if slot:
+            self._release(slot)
+        cap = max(1 << 20, (rows + (rows >> 3) + (1 << 20) - 1) >> 20 << 20)
+        ptr, h = self.ops.peer_alloc(cap * 8)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, h, group=self.group)
+        peers = [ptr if r == self.rank else self.ops.peer_open(hh) for r, hh in enumerate(handles)]
+        slot = {"cap": cap, "itemsize": 8, "pairs": True, "mine": (ptr,), "peers": (peers,)}
+        self.slots[name] = slot
+        return slot
+
+    def fused_inner_join(self, probe_keys, build_keys, probe_offset, build_offset, timings=None):
+        """INNER join with ONE partition pass per side: every rank histograms both sides with the combined
+        (destination rank x receiver-local partition) geometry, ONE all_gather carries both count matrices, ONE
+        scatter per side stores compact pairs into the peers' partition-contiguous buffers over NVLink, and the
+        receiver joins what it got without partitioning again.  Returns None when the compact form does not apply
+        (a build key wider than 32 bits, a partition too large): the caller then takes the two-pass path."""
+        world, rank, dev = self.world, self.rank, probe_keys.device
+        ev = _Stamps(timings, dev)
+        sizes = torch.tensor([build_keys.numel()], dtype=torch.int64, device=dev)
+        dist.all_reduce(sizes, group=self.group)
+        nlocal = fused_nlocal(int(sizes.item()), world)
+        bins = world * nlocal
+        cb, hi_b = self.ops.xjoin_count(build_keys, world, nlocal)
+        cp, _ = self.ops.xjoin_count(probe_keys, world, nlocal)
+        mine = torch.tensor(cb + cp + [hi_b], dtype=torch.int64, device=dev)
+        allc = torch.empty(world * (2 * bins + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)     # also: everybody is done with the previous buffers
+        M = allc.view(world, 2 * bins + 1).cpu().tolist()
+        if any(row[2 * bins] for row in M):
+            return None
+        off_b, tot_b, recv_b = plan_fused_exchange([row[:bins] for row in M], world, nlocal, rank)
+        off_p, tot_p, recv_p = plan_fused_exchange([row[bins:2 * bins] for row in M], world, nlocal, rank)
+        if max(tot_b) > (1 << 22):
+            return None
+        sb, sp = self._ensure_pairs("xbuild", max(recv_b)), self._ensure_pairs("xprobe", max(recv_p))
+        ev.mark("count+plan")
+        self.ops.xjoin_scatter(build_keys, build_offset, world, nlocal, sb["peers"][0], off_b)
+        self.ops.xjoin_scatter(probe_keys, probe_offset, world, nlocal, sp["peers"][0], off_p)
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(self._flag, group=self.group)                 # stream-ordered: every rank's stores have landed
+        ev.mark("partition+exchange")
+        out = self.ops.xjoin_local(sp["mine"][0], tot_p, sb["mine"][0], tot_b, nlocal)
+        ev.mark("local_join")
+        return out
 
     def exchange_pairs(self, name, keys, id_base):
         """Returns (keys, ids) this rank received: zero-copy views of its receive buffers, valid until the
@@ -311,6 +387,38 @@ class PeerExchange(object):
         n = int(recv_totals[rank].item())
         np_key = {8: np.int64, 4: np.int32}[keys.element_size()]
         return self.ops.view(slot["mine"][0], n, np_key), self.ops.view(slot["mine"][1], n, np.int32)
+
+
+def plan_fused_exchange(counts, world, nlocal, rank):
+    """Host-side plan of the one-pass exchange.  counts[s][d * nlocal + p] = pairs rank s sends to (rank d, local
+    partition p).  Receiver d lays its buffer out partition-major, and inside a partition in sender order, so
+        offsets[d * nlocal + p]  where THIS rank's pairs of bin (d, p) start inside d's buffer
+        part_totals[p]           pairs of local partition p this rank receives (all senders)
+        recv_rows[d]             total pairs rank d receives (buffer sizing)
+    Pure arithmetic on the gathered count matrix: every rank computes the same plan (tests/test_dist_cpu.py)."""
+    offsets, recv_rows = [0] * (world * nlocal), [0] * world
+    for d in range(world):
+        run = 0
+        for p in range(nlocal):
+            b = d * nlocal + p
+            offsets[b] = run + sum(counts[s][b] for s in range(rank))
+            run += sum(counts[s][b] for s in range(world))
+        recv_rows[d] = run
+    part_totals = [sum(counts[s][rank * nlocal + p] for s in range(world)) for p in range(nlocal)]
+    return offsets, part_totals, recv_rows
+
+
+def fused_nlocal(build_rows_total, world, rows_per_partition=1 << 20, max_bins=256):
+    """Receiver-local radix partitions for the one-pass exchange: a power of two such that one partition holds about
+    2^20 build rows (table <= 16 MB, L2-resident), limited by the 256 bins one partition pass can write."""
+    per_rank = (build_rows_total + world - 1) // world
+    want = max(1, (per_rank + rows_per_partition - 1) // rows_per_partition)
+    n = 1
+    while n < want:
+        n *= 2
+    while n * world > max_bins and n > 1:
+        n //= 2
+    return n
 
 
 def shard_bounds(total_rows, world, rank):
@@ -338,7 +446,16 @@ def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops
     if max(left_offset + left_keys.numel(), right_offset + right_keys.numel()) >= 2 ** 31:
         raise ValueError("global row ids must fit int32 (gdf join indices are GDF_INT32)")
     fn = ops.inner_join if kind == "inner" else ops.left_join
-    if peer is not None:   # fused partition + exchange over NVLink peer memory (PeerExchange)
+    if peer is not None and kind == "inner" and getattr(peer, "one_pass", True):
+        # one partition pass per side: the build side is the smaller table (gdf_inner_join's rule, joining.h:59-67)
+        sizes = torch.tensor([left_keys.numel(), right_keys.numel()], dtype=torch.int64, device=dev)
+        dist.all_reduce(sizes, group=group)
+        flip = int(sizes[1].item()) > int(sizes[0].item())
+        out = (peer.fused_inner_join(right_keys, left_keys, right_offset, left_offset, timings) if flip
+               else peer.fused_inner_join(left_keys, right_keys, left_offset, right_offset, timings))
+        if out is not None:
+            return (out[1], out[0]) if flip else out
+    if peer is not None:   # two-pass path: partition + exchange over NVLink peer memory, then the local partitioned join
         lk, li = peer.exchange_pairs("left", left_keys, left_offset)
         rk, ri = peer.exchange_pairs("right", right_keys, right_offset)
         ev.mark("partition+exchange")
@@ -357,7 +474,7 @@ def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops
 
 
 def distributed_left_join_masked(left_keys, left_valids, right_keys, right_valids, left_offset, right_offset, ops,
-                                 group=None, timings=None):
+                                 group=None, timings=None, peer=None):
     """LEFT hash join on a COMPOSITE key with NULLs (BASELINE config C5: (int64,int32) key, 30 % null rows).
 
     left_keys / right_keys     lists of this rank's key-column shards

