@@ -18,6 +18,16 @@ size_t gdfx_trim_scratch(void);
 size_t gdfx_scratch_cached_bytes(void);
 void gdfx_set_scratch_limit(size_t bytes);
 
+/* gdf_filter on one aligned column runs a persistent kernel whose chunk look-back needs forward progress of the CTAs
+ * holding earlier chunks (csrc/select_stream.cuh).  mode 0 (default): static chunk dealing under a COOPERATIVE launch
+ * (the driver starts the grid only once all of its CTAs fit), falling back to mode 1 when the device refuses one;
+ * mode 1: chunks are taken through an atomic ticket, which needs no co-residency at all (about 20 % slower at 1e9
+ * rows).  Returns the previous mode.  gdfx_debug_occupy_sms is a TEST helper: it parks `blocks` CTAs that fill an SM
+ * each (1024 threads, 200 KB of shared memory) on a private non-blocking stream for about `microseconds`, so that a
+ * test can run gdf_filter while a foreign kernel holds part of the GPU (tests/test_filter_gpu.py). */
+int gdfx_set_select_dealing(int mode);
+gdf_error gdfx_debug_occupy_sms(int blocks, unsigned microseconds);
+
 /* Multi-GPU layer helper (libgdf_b200/dist.py): indices[i] = payload[indices[i]] in place for every
  * non-negative entry (< payload_rows), -1 otherwise.  `indices` is a GDF_INT32 join output column;
  * `payload` is a device array of the global row ids that travelled with the exchanged keys. */

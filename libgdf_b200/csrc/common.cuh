@@ -39,6 +39,8 @@ namespace b200 {
 // device properties (cached per device)
 // ----------------------------------------------------------------------------------------------
 int sm_count();  // 148 on B200; queried once per device
+int select_dealing_mode();      // gdfx_set_select_dealing (include/gdf_b200_ext.h): 0 cooperative + static, 1 ticket
+bool cooperative_launch_ok();  // cudaDevAttrCooperativeLaunch: a cooperative grid is only started once ALL its CTAs fit
 
 // Width in bytes of a gdf dtype, 0 if the dtype has no fixed width on this path
 // (ref src/column.cpp:237-275).

@@ -119,7 +119,8 @@ struct StencilPolicy {
   const gdf_valid_type* svalid;
   const T* data;
   T* out;
-  bool vec_ok;
+  bool vec_ok;        // the stencil bytes can be read with 128-bit loads
+  bool data_vec_ok;   // so can the data column
 
   __device__ uint32_t flags(size_t warp_base, size_t n) const {
     const unsigned lane = lane_id();
@@ -150,6 +151,50 @@ struct StencilPolicy {
     return f;
   }
   __device__ void emit(size_t row, size_t pos) const { out[pos] = data[row]; }
+  // A step is 32 lanes x V = 512 consecutive rows.  At C2's 10 % selectivity a per-row gather touches 81 % of the
+  // column's 128-byte lines anyway (ncu: 7.7 GB of DRAM reads for 0.8 GB of selected values) and does so with one
+  // divergent request per row; so when a step has >= kDenseMin selected rows the warp streams the step's rows with
+  // coalesced 128-bit loads instead - instruction i covers the 32 consecutive 16-byte pieces i * 32 + lane - and every
+  // lane fetches the flag bits and output position of the piece's OWNER lane with two shuffles.
+  static constexpr uint32_t kDenseMin = 16;
+  __device__ bool emit_dense(size_t step_row0, size_t n, uint32_t my_bits, size_t my_pos, uint32_t step_total) const {
+    constexpr int E = 16 / (int)sizeof(T);   // rows per 16-byte piece
+    constexpr int I = V / E;                 // pieces per lane = load instructions per step
+    if (!data_vec_ok || step_total < kDenseMin || step_row0 + (size_t)32 * V > n) return false;  // warp-uniform
+    const unsigned lane = lane_id();
+    const uint4* src = reinterpret_cast<const uint4*>(data + step_row0);
+    constexpr int B = I < 4 ? I : 4;         // loads in flight per lane (8 x 16 bytes spilled at 3 CTAs per SM)
+#pragma unroll
+    for (int i0 = 0; i0 < I; i0 += B) {
+      uint4 raw[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) raw[i] = ldg_stream(src + (i0 + i) * 32 + lane);
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        const unsigned piece = (unsigned)(i0 + i) * 32u + lane;
+        const unsigned owner = piece / I, sub = piece % I;
+        const uint32_t obits = __shfl_sync(0xffffffffu, my_bits, owner);
+        const unsigned long long opos = __shfl_sync(0xffffffffu, (unsigned long long)my_pos, owner);
+        const uint32_t mine = (obits >> (sub * E)) & ((1u << E) - 1u);
+        size_t p = (size_t)opos + __popc(obits & ((1u << (sub * E)) - 1u));
+        const T* e = reinterpret_cast<const T*>(&raw[i]);
+#pragma unroll
+        for (int j = 0; j < E; ++j)
+          if ((mine >> j) & 1u) out[p++] = e[j];
+      }
+    }
+    return true;
+  }
+  // few selected rows: all gathers of the lane's step in flight before the first store (select_chunked.cuh: emit_step)
+  __device__ void emit_step(size_t row0, uint32_t bits, size_t pos) const {
+    T v[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      if ((bits >> j) & 1u) v[j] = data[row0 + j];
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      if ((bits >> j) & 1u) out[pos++] = v[j];
+  }
 };
 
 // gdf_filter, one 16-byte aligned column: streaming kernel (select_stream.cuh)
@@ -186,18 +231,36 @@ gdf_error run_filter_stream(const T* data, size_t n, const void* const* d_vals, 
   uint64_t* d = desc.as<uint64_t>();
   unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + chunks);
   unsigned* d_ticket = reinterpret_cast<unsigned*>(d_count + 1);
-  auto kern = select_stream::select_stream_kernel<T, EqualsDeviceScalar<T>, EmitRowIndex>;
+  // Two dealings of the same kernel (select_stream.cuh).  STATIC (CTA b: chunks b, b + grid, ...) is the faster one
+  // - 1.54 ms against 1.83-1.89 ms at C2 for every placement of the ticket atomic that was tried (profiles/
+  // r02_notes.md) - but its look-back only makes progress if the whole grid is co-resident.  A COOPERATIVE launch
+  // makes that a guarantee of the driver instead of an assumption (the grid is not started until every CTA fits, even
+  // when another stream's persistent kernel holds SMs).  When the device refuses a cooperative launch, the TICKET
+  // dealing runs: chunks are handed out in increasing order to CTAs that are already running, so it needs no
+  // co-residency at all.
+  auto kern_static = select_stream::select_stream_kernel<T, EqualsDeviceScalar<T>, EmitRowIndex, true>;
+  auto kern_ticket = select_stream::select_stream_kernel<T, EqualsDeviceScalar<T>, EmitRowIndex, false>;
   const int smem = (int)select_stream::smem_bytes<T>();
-  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  int per_sm = 0;  // persistent CTAs: one resident wave (chunk tickets keep the look-back live even if fewer run)
-  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, select_stream::kThreads, smem));
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern_static, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern_ticket, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;  // persistent CTAs: one resident wave
+  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_static, select_stream::kThreads, smem));
   B200_REQUIRE(per_sm >= 1, GDF_CUDA_ERROR);
   const size_t resident = (size_t)sm_count() * (size_t)per_sm;
   const unsigned blocks = (unsigned)(chunks < resident ? chunks : resident);
+  EqualsDeviceScalar<T> pred{d_vals, T()};
+  EmitRowIndex emit{out};
+  bool launched = false;
   {
     B200_TIMED("select");
-    kern<<<blocks, select_stream::kThreads, smem>>>(data, n, EqualsDeviceScalar<T>{d_vals, T()}, EmitRowIndex{out}, d,
-                                                    d_count, d_ticket);
+    if (cooperative_launch_ok() && select_dealing_mode() == 0) {
+      void* args[] = {(void*)&data, (void*)&n, (void*)&pred, (void*)&emit, (void*)&d, (void*)&d_count, (void*)&d_ticket};
+      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)kern_static, dim3(blocks), dim3(select_stream::kThreads), args,
+                                                         (size_t)smem, 0);
+      if (ce == cudaSuccess) launched = true;
+      else (void)cudaGetLastError();  // refused (e.g. MPS / partitioned device): the ticket dealing needs no guarantee
+    }
+    if (!launched) kern_ticket<<<blocks, select_stream::kThreads, smem>>>(data, n, pred, emit, d, d_count, d_ticket);
   }
   B200_CHECK_LAST();
   return read_count(d_count, h_count);
@@ -419,6 +482,7 @@ gdf_error stencil_typed(gdf_column* lhs, gdf_column* stencil, gdf_column* out, s
   pol.data = static_cast<const T*>(lhs->data);
   pol.out = static_cast<T*>(out->data);
   pol.vec_ok = aligned16(stencil->data);
+  pol.data_vec_ok = aligned16(lhs->data);
   return run_select(pol, (size_t)lhs->size, count);
 }
 

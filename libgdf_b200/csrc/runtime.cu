@@ -29,6 +29,20 @@ int sm_count() {
   return cached[dev];
 }
 
+static int g_select_dealing = 0;
+int select_dealing_mode() { return g_select_dealing; }
+
+bool cooperative_launch_ok() {
+  static int cached[64] = {0};  // 0 unknown, 1 yes, 2 no
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (cached[dev] == 0) {
+    int v = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 2;
+  }
+  return cached[dev] == 1;
+}
+
 static BlockCache& scratch_cache() {
   static BlockCache* c = new BlockCache();  // leaked on purpose: no teardown-order issues at exit
   return *c;
@@ -131,6 +145,33 @@ extern "C" size_t gdfx_trim_scratch() {
 }
 extern "C" size_t gdfx_scratch_cached_bytes() { return b200::scratch_cache().cached_bytes(); }
 extern "C" void gdfx_set_scratch_limit(size_t bytes) { b200::scratch_cache().set_limit(bytes); }
+
+extern "C" int gdfx_set_select_dealing(int mode) {
+  const int prev = b200::g_select_dealing;
+  b200::g_select_dealing = mode ? 1 : 0;
+  return prev;
+}
+
+// TEST helper (include/gdf_b200_ext.h): CTAs that fill one SM each, parked for a while on a private non-blocking stream
+static __global__ void __launch_bounds__(1024, 1) occupy_kernel(unsigned long long ns) {
+  extern __shared__ unsigned char occupy_smem[];
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+  if (ns == ~0ull) occupy_smem[threadIdx.x] = 0;  // keeps the shared-memory allocation alive
+}
+extern "C" gdf_error gdfx_debug_occupy_sms(int blocks, unsigned microseconds) {
+  if (blocks <= 0) return GDF_SUCCESS;
+  static cudaStream_t side = nullptr;
+  if (side == nullptr) B200_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  const int smem = 200 * 1024;
+  B200_CUDA_TRY(cudaFuncSetAttribute(occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  occupy_kernel<<<blocks, 1024, smem, side>>>((unsigned long long)microseconds * 1000ull);
+  B200_CHECK_LAST();
+  return GDF_SUCCESS;
+}
 
 extern "C" int gdfx_profile_enable(int on) {
   b200::Profiler& p = b200::prof();

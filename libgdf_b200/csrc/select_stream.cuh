@@ -28,6 +28,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStages = 3;
 constexpr int kChunkTiles = 16;
+constexpr int kTicketTile = kChunkTiles - kStages - 3;   // tile after which the next chunk's ticket is taken (see below)
 
 template <typename T>
 struct Geom {
@@ -43,7 +44,7 @@ struct Smem {
   uint64_t bar[kStages];
   uint32_t warp_tot[kChunkTiles][kWarps];
   uint64_t chunk_excl;
-  unsigned chunk_ids[2];   // tickets of this CTA's current and next chunk (index: CTA-local chunk number & 1)
+  unsigned chunk_cur;      // ticket of the chunk the CTA is about to process (written by thread 0 one barrier earlier)
 };
 
 template <typename T>
@@ -103,7 +104,15 @@ static __device__ __forceinline__ uint64_t lookback_wide(uint64_t* desc, unsigne
 // every predecessor of a chunk is held by a running CTA: the look-back always makes progress, whether or not the
 // whole grid is co-resident (another stream's persistent kernel may hold SMs).  Round 1 dealt chunks statically
 // (CTA b: b, b + grid, ...), which was only safe with the full grid resident.
-template <typename T, typename Pred, typename Emit>
+// WHEN the ticket is taken matters (profiles/r02_notes.md): a CTA that reserves its next chunk at the START of the
+// current one holds that chunk idle for a whole chunk time while CTAs with later tickets already wait for its
+// aggregate in their look-back - with two CTAs per SM the two waves ended up alternating (one streams, the other
+// waits), C2 1.54 -> 1.87 ms.  The ticket is therefore taken as late as the prefetch allows: after tile
+// kTicketTile = 10, three tiles (~5 us, well above the atomic's latency) before tile 13's prefetch needs it.  Only
+// thread 0 starts copies, so the ticket lives in one of its registers and reaches the other threads through shared
+// memory at the chunk's last barrier; nothing ever waits for the atomic.
+// STATIC_DEAL = round 1's dealing, kept for A/B in the lab build only.
+template <typename T, typename Pred, typename Emit, bool STATIC_DEAL = false>
 __global__ void __launch_bounds__(kThreads)
 select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit, uint64_t* __restrict__ desc,
                      unsigned long long* __restrict__ count_out, unsigned* __restrict__ ticket) {
@@ -117,12 +126,11 @@ select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit,
   pred.prepare();
 
   // The CTA's tiles form one sequence q = 0, 1, 2, ...: tile q is tile (q % 16) of the CTA's (q / 16)-th chunk and
-  // lives in ring stage q % kStages.  Only thread 0 calls this (it is the thread that takes the tickets).
-  auto tile_index = [&](unsigned q) {
-    return (size_t)sm.chunk_ids[(q / kChunkTiles) & 1u] * kChunkTiles + (q % kChunkTiles);
-  };
-  auto issue = [&](unsigned q) {  // one thread starts the copy of the CTA's q-th tile (full tiles only)
-    const size_t t = tile_index(q);
+  // lives in ring stage q % kStages.  Only thread 0 starts copies; it holds the tickets of the CTA's current and
+  // next chunk in registers (ids[CTA-local chunk number & 1]).
+  unsigned id_cur = 0u, id_next = 0u;   // id_next is written by the atomic and not touched until tile 13's prefetch
+  auto issue = [&](unsigned q, bool next_chunk) {  // thread 0 starts the copy of the CTA's q-th tile (full tiles only)
+    const size_t t = (size_t)(next_chunk ? id_next : id_cur) * kChunkTiles + (q % kChunkTiles);
     const int s = (int)(q % kStages);
     if (t < tiles && (t + 1) * G::kTileRows <= n) {
       tma::mbar_expect_tx(&sm.bar[s], G::kTileBytes);
@@ -133,18 +141,18 @@ select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit,
 #pragma unroll
     for (int s = 0; s < kStages; ++s) tma::mbar_init(&sm.bar[s], 1);
     tma::fence_barrier_init();
-    sm.chunk_ids[0] = atomicAdd(ticket, 1u);
+    id_cur = STATIC_DEAL ? blockIdx.x : atomicAdd(ticket, 1u);
+    sm.chunk_cur = id_cur;
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) issue((unsigned)s);
+    for (int s = 0; s < kStages; ++s) issue((unsigned)s, false);
   }
   __syncthreads();
 
   unsigned q = 0;                  // tiles consumed so far by this CTA
   unsigned phase_bits = 0;         // bit s = parity the next FULL tile of stage s completes
   for (unsigned j = 0;; ++j) {     // j = CTA-local chunk number
-    const size_t chunk = sm.chunk_ids[j & 1u];
+    const size_t chunk = sm.chunk_cur;
     if (chunk >= chunks) break;
-    if (tid == 0) sm.chunk_ids[(j + 1) & 1u] = atomicAdd(ticket, 1u);  // next chunk: needed by the prefetch from tile 13 on
     uint32_t f[kChunkTiles], excl[kChunkTiles];
 #pragma unroll
     for (int k = 0; k < kChunkTiles; ++k, ++q) {
@@ -180,7 +188,8 @@ select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit,
       excl[k] = inc - __popc(bits);
       if (lane == 31) sm.warp_tot[k][warp] = inc;
       __syncthreads();  // every thread is done with stage s (and, for k = 15, all warp totals are visible)
-      if (tid == 0) issue(q + kStages);
+      if (k == kTicketTile && tid == 0) id_next = STATIC_DEAL ? (unsigned)chunk + gridDim.x : atomicAdd(ticket, 1u);
+      if (tid == 0) issue(q + kStages, k + kStages >= kChunkTiles);
     }
     if (warp == 0) {
       uint32_t part = 0;
@@ -216,7 +225,8 @@ select_stream_kernel(const T* __restrict__ data, size_t n, Pred pred, Emit emit,
         emit(row0 + i, pos++);
       }
     }
-    __syncthreads();  // warp_tot / chunk_excl are rewritten by the next chunk
+    if (tid == 0) sm.chunk_cur = id_cur = id_next;
+    __syncthreads();  // warp_tot / chunk_excl are rewritten by the next chunk; chunk_cur is visible
   }
 }
 

@@ -162,3 +162,54 @@ def test_sharded_c5_left_join_composite_key_with_nulls(world):
     ol, orr = oracle.join(oracle.JOIN_LEFT, l, r, lv, rv)
     got, want = np.stack([gl, gr], 1), np.stack([ol, orr], 1)
     np.testing.assert_array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
+
+
+@pytest.mark.parametrize("world,nlocal", [(2, 1), (2, 8), (3, 4), (8, 16), (8, 32)])
+@pytest.mark.parametrize("key_dtype", [np.int64, np.int32])
+def test_one_pass_fused_exchange_matches_oracle(world, nlocal, key_dtype):
+    """PeerExchange.fused_inner_join on ONE GPU: `world` virtual ranks count with the combined (destination rank x
+    receiver-local partition) geometry, derive the plan from the gathered count matrix, scatter compact pairs
+    straight into the destinations' buffers (local tensors here; IPC-mapped peer memory in a real run) and every
+    virtual rank joins what it received WITHOUT partitioning again.  Union == the single-table oracle join."""
+    ops = D.GdfOps()
+    P, B = 400_003, 60_000
+    probe = np.random.randint(0, 2 * B, P).astype(key_dtype)
+    build = np.random.permutation(B).astype(key_dtype)
+    bins = world * nlocal
+    shards, counts_b, counts_p = [], [], []
+    for r in range(world):
+        plo, phi = D.shard_bounds(P, world, r)
+        blo, bhi = D.shard_bounds(B, world, r)
+        pk, bk = torch.from_numpy(probe[plo:phi]).cuda(), torch.from_numpy(build[blo:bhi]).cuda()
+        cb, hi_b = ops.xjoin_count(bk, world, nlocal)
+        cp, _ = ops.xjoin_count(pk, world, nlocal)
+        assert hi_b == 0 and sum(cb) == bhi - blo and sum(cp) == phi - plo and len(cb) == bins
+        shards.append((pk, plo, bk, blo)), counts_b.append(cb), counts_p.append(cp)
+    plans_b = [D.plan_fused_exchange(counts_b, world, nlocal, r) for r in range(world)]
+    plans_p = [D.plan_fused_exchange(counts_p, world, nlocal, r) for r in range(world)]
+    pad = 5                                                      # sentinel pairs behind every receive buffer
+    buf_b = [torch.full((plans_b[0][2][d] + pad, 2), -7, dtype=torch.int32, device="cuda") for d in range(world)]
+    buf_p = [torch.full((plans_p[0][2][d] + pad, 2), -7, dtype=torch.int32, device="cuda") for d in range(world)]
+    for r, (pk, plo, bk, blo) in enumerate(shards):
+        ops.xjoin_scatter(bk, blo, world, nlocal, [t.data_ptr() for t in buf_b], plans_b[r][0])
+        ops.xjoin_scatter(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], plans_p[r][0])
+    torch.cuda.synchronize()
+    got_l, got_r = [], []
+    for d in range(world):
+        assert (buf_b[d][-pad:] == -7).all() and (buf_p[d][-pad:] == -7).all()          # nothing written past the plan
+        assert (buf_b[d][:-pad, 1] >= 0).all() and (buf_p[d][:-pad, 1] >= 0).all()      # no hole left inside it
+        gl, gr = ops.xjoin_local(buf_p[d].data_ptr(), plans_p[d][1], buf_b[d].data_ptr(), plans_b[d][1], nlocal)
+        got_l.append(gl.cpu().numpy()), got_r.append(gr.cpu().numpy())
+    gl, gr = np.concatenate(got_l), np.concatenate(got_r)
+    ol, orr = oracle.join(oracle.JOIN_INNER, [probe.astype(np.int64)], [build.astype(np.int64)])
+    got, want = np.stack([gl, gr], 1), np.stack([ol, orr], 1)
+    np.testing.assert_array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
+
+
+def test_one_pass_fused_exchange_reports_wide_keys():
+    """A build key that does not fit 32 bits makes the compact exchange inapplicable: xjoin_count says so (hi_or != 0)
+    and PeerExchange falls back to the two-pass path."""
+    ops = D.GdfOps()
+    keys = torch.tensor([1, 2, (1 << 40) + 3, 4], dtype=torch.int64, device="cuda")
+    counts, hi = ops.xjoin_count(keys, 2, 4)
+    assert hi != 0 and sum(counts) == 3          # the wide key is counted nowhere, exactly as the scatter drops it

@@ -209,3 +209,58 @@ def test_stencil_errors():
     with pytest.raises(GDFError) as e:
         libgdf.gpu_apply_stencil(L.cdata, S.cdata, O.cdata)
     assert e.value.errcode == "GDF_VALIDITY_UNSUPPORTED"
+
+
+# ---- forward progress of the streaming select ----
+def _filter_big(n, seed=3):
+    col = torch.randint(0, 10, (n,), generator=torch.Generator(device="cuda").manual_seed(seed), device="cuda", dtype=torch.int64)
+    c = C.Column(col)
+    structs = C.struct_array([c])
+    d_cols = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_types = torch.zeros(1, dtype=torch.int32, device="cuda")
+    val = torch.tensor([3], dtype=torch.int64, device="cuda")
+    d_vals = torch.tensor([val.data_ptr()], dtype=torch.int64, device="cuda")
+    d_indx = torch.empty(n, dtype=torch.int64, device="cuda")
+    new_sz = ffi.new("size_t*")
+
+    def run():
+        libgdf.gdf_filter(n, structs, 1, ffi.cast("void**", d_cols.data_ptr()), ffi.cast("int*", d_types.data_ptr()),
+                          ffi.cast("void**", d_vals.data_ptr()), ffi.cast("size_t*", d_indx.data_ptr()), new_sz)
+        return d_indx[: int(new_sz[0])].clone()
+    want = torch.nonzero(col == 3).flatten()
+    return run, want
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_filter_both_chunk_dealings_agree_at_many_chunks_per_cta(mode):
+    """40 M rows = 611 chunks for at most 296 persistent CTAs: every CTA takes several chunks, so the static dealing
+    (cooperative launch) and the ticket dealing both run their steady state.  Bit-exact and ascending."""
+    run, want = _filter_big(40_000_003)
+    prev = libgdf.gdfx_set_select_dealing(mode)
+    try:
+        got = run()
+    finally:
+        libgdf.gdfx_set_select_dealing(prev)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("held_sms", [74, 140])
+def test_filter_completes_while_a_foreign_kernel_holds_sms(mode, held_sms):
+    """A foreign kernel parks CTAs that fill `held_sms` SMs for ~40 ms on another (non-blocking) stream, so the select's
+    persistent grid cannot be co-resident while it runs.  Mode 0: the cooperative launch is simply not started until
+    the grid fits; mode 1: the ticket dealing makes progress on whatever SMs are free.  Neither may hang or mis-rank."""
+    run, want = _filter_big(30_000_001, seed=9)
+    run()                                            # warm: scratch allocation, attribute calls
+    prev = libgdf.gdfx_set_select_dealing(mode)
+    try:
+        libgdf.gdfx_debug_occupy_sms(held_sms, 40_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        got = run()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        libgdf.gdfx_set_select_dealing(prev)
+    assert torch.equal(got, want)
+    print("mode %d, %d SMs held: gdf_filter returned after %.2f ms" % (mode, held_sms, e0.elapsed_time(e1)))
