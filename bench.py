@@ -55,6 +55,11 @@ def parse_args():
                     help="N>1: rows cross NVLink inside the partition kernel (peer memory) or via NCCL all_to_all")
     ap.add_argument("--lab", action="store_true", help="load the -DB200_LAB build (libgdf_b200/lib_lab, make LAB=1): "
                     "environment-variable knobs and timing ablations; never a bench value")
+    ap.add_argument("--xjoin-rpp-log2", type=int, default=0, help="N > 1: log2 of the build rows per receiver-local partition of "
+                    "the one-pass exchange (0 = library default)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: fill the hash tables after the exchange instead of beside it")
+    ap.add_argument("--scatter-ctas", type=int, default=-1, help="N > 1: CTAs per SM of the probe-side scatter while the tables are built (0 = all)")
+    ap.add_argument("--two-pass", action="store_true", help="N > 1: round 1's exchange (partition by destination, then again locally)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -714,6 +719,12 @@ def bench_dist(args, rank, world, local_rank):
     if args.exchange == "p2p":
         if D.PeerExchange.available(ops):
             peer = D.PeerExchange(ops)
+            peer.one_pass = not args.two_pass
+            peer.overlap_build = not args.no_overlap
+            if args.scatter_ctas >= 0:
+                peer.scatter_ctas_per_sm = args.scatter_ctas
+            if args.xjoin_rpp_log2:
+                peer.rows_per_partition = 1 << args.xjoin_rpp_log2
         elif rank == 0:
             print("bench.py: CUDA IPC peer mapping unavailable on this box, falling back to --exchange nccl", file=sys.stderr)
     peak_gbs, peak_kind = load_peak()
@@ -752,7 +763,7 @@ def bench_dist(args, rank, world, local_rank):
     timings = {}
 
     def step():
-        a, b = D.distributed_join("inner", probe, build, plo, blo, ops, timings=timings, peer=peer)
+        a, b = D.distributed_join("inner", probe, build, plo, blo, ops, timings=timings, peer=peer, global_rows=(P, B))
         del a, b
 
     def timed(fn, warmup, steps):
@@ -796,7 +807,7 @@ def bench_dist(args, rank, world, local_rank):
         def e2e_step():
             d_probe.copy_(h_probe, non_blocking=True)
             d_build.copy_(h_build, non_blocking=True)
-            a, b = D.distributed_join("inner", d_probe, d_build, plo, blo, ops, peer=peer)
+            a, b = D.distributed_join("inner", d_probe, d_build, plo, blo, ops, peer=peer, global_rows=(P, B))
             h_l[: a.numel()].copy_(a, non_blocking=True)
             h_r[: b.numel()].copy_(b, non_blocking=True)
             torch.cuda.synchronize()

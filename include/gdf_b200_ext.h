@@ -80,6 +80,28 @@ gdf_error gdfx_peer_free(void *ptr);
 gdf_error gdfx_xjoin_count(gdf_column *key, int ranks, int nlocal, unsigned long long *counts, unsigned *hi_or);
 gdf_error gdfx_xjoin_scatter(gdf_column *key, int32_t id_base, int ranks, int nlocal, void * const *dst_pairs,
                              const unsigned long long *dst_offsets);
+/* The same exchange WITHOUT host round trips between the histogram and the scatter: counts stay on the device
+ * (d_counts[ranks * nlocal + 1]: the bins, then the OR of the keys' high words), the caller all-gathers
+ * {build counts | probe counts} of every rank into d_all[ranks][2 * (ranks * nlocal + 1)], gdfx_xjoin_plan_dev turns
+ * that into this rank's write offsets on the device (and raises d_status[0] = wide build keys, d_status[1] = a
+ * receive buffer of cap_build / cap_probe pairs would overflow), and gdfx_xjoin_scatter_dev reads offsets and status
+ * from the device - it writes nothing when a status flag is set, so the caller can check the flags AFTER launching.
+ * ctas_per_sm > 0 caps the scatter's resident CTAs per SM (it is NVLink-bound; the rest of the SM is left to a kernel
+ * running beside it, see gdfx_xjoin_build). */
+gdf_error gdfx_xjoin_count_dev(gdf_column *key, int ranks, int nlocal, unsigned long long *d_counts);
+gdf_error gdfx_xjoin_plan_dev(const unsigned long long *d_all, int ranks, int nlocal, int rank, unsigned long long cap_build,
+                              unsigned long long cap_probe, unsigned long long *d_off_build, unsigned long long *d_off_probe,
+                              int *d_status);
+gdf_error gdfx_xjoin_scatter_dev(gdf_column *key, int32_t id_base, int ranks, int nlocal, void * const *dst_pairs,
+                                 const unsigned long long *d_offsets, const int *d_status, int ctas_per_sm);
+/* gdfx_xjoin_local in two stages, so that a rank fills its hash tables WHILE the probe side is still crossing NVLink:
+ * gdfx_xjoin_build is ordered after everything issued so far on the legacy stream (i.e. after the build side's
+ * exchange) and, with overlap != 0, runs on a private non-blocking stream; gdfx_xjoin_probe makes the legacy stream wait
+ * for it, probes, fills the outputs and releases the handle (it must be called exactly once per successful build). */
+gdf_error gdfx_xjoin_build(const void *build_pairs, const unsigned long long *build_counts, int nlocal, int overlap,
+                           void **handle);
+gdf_error gdfx_xjoin_probe(void *handle, const void *probe_pairs, const unsigned long long *probe_counts,
+                           gdf_column *out_l, gdf_column *out_r);
 gdf_error gdfx_xjoin_local(const void *probe_pairs, const unsigned long long *probe_counts, const void *build_pairs,
                            const unsigned long long *build_counts, int nlocal, gdf_column *out_l, gdf_column *out_r);
 

@@ -102,6 +102,38 @@ def library_owned_to_torch(cdata, api=None):
     return out
 
 
+class _OwnedAlias(object):
+    """__cuda_array_interface__ view of a library-allocated column that frees it (gdf_column_free -> rmmFree, reference
+    src/column.cpp:222-227) when the last tensor built on it goes away: torch keeps the producer object alive."""
+
+    def __init__(self, cdata, np_dtype, api):
+        self._api = api
+        self._col = ffi.new("gdf_column*")
+        self._col[0] = cdata[0]          # own a copy of the struct: the caller's gdf_column may be reused
+        n = int(cdata.size)
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(np_dtype).str,
+                                         "data": (int(ffi.cast("uintptr_t", cdata.data)), False), "version": 2, "strides": None}
+
+    def __del__(self):
+        try:
+            if self._col.data != ffi.NULL:
+                self._api.gdf_column_free(self._col)
+        except Exception:      # interpreter shutdown
+            pass
+
+
+def library_owned_view(cdata, api=None):
+    """Zero-copy torch view of a library-allocated GDF_INT32 column (join output); the memory is handed back with
+    gdf_column_free when the tensor dies.  No copy, no synchronisation (library_owned_to_torch does both)."""
+    api = api or libgdf
+    n = int(cdata.size)
+    if n == 0:
+        if cdata.data != ffi.NULL:
+            api.gdf_column_free(cdata)
+        return torch.empty(0, dtype=torch.int32, device="cuda")
+    return torch.as_tensor(_OwnedAlias(cdata, np.int32, api), device="cuda")
+
+
 class _Alias(object):
     def __init__(self, address, shape, dtype):
         self.__cuda_array_interface__ = {"shape": shape, "typestr": np.dtype(dtype).str,

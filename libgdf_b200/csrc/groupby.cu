@@ -221,7 +221,7 @@ __global__ void init_fast_kernel(unsigned long long* keys, int64_t* acc, unsigne
 }
 
 // 64-bit wrapping add in SHARED memory built from 32-bit atomics: on B200 a 32-bit shared atomic
-// runs ~8x faster than a 64-bit one (profiles/r01_microbench.txt: ~2900 vs ~400 Gop/s), and for
+// runs ~8x faster than a 64-bit one (profiles/r02_microbench.txt: ~2900 vs ~400 Gop/s), and for
 // small non-negative addends the high word is touched only on a carry.
 static __device__ __forceinline__ void smem_add64(unsigned long long* acc, int64_t v) {
   unsigned* w = reinterpret_cast<unsigned*>(acc);

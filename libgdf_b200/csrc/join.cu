@@ -47,7 +47,14 @@ gdf_error partition_scatter_peer(const gdf_column* key, int32_t id_base, unsigne
                                  int32_t* const* dst_ids, const unsigned long long* dst_offsets);
 gdf_error xjoin_count(const gdf_column* key, unsigned ranks, unsigned nlocal, unsigned long long* h_counts, unsigned* hi_or);
 gdf_error xjoin_scatter(const gdf_column* key, int32_t id_base, unsigned ranks, unsigned nlocal, void* const* dst_pairs,
-                        const unsigned long long* h_offsets);
+                        const unsigned long long* h_offsets, const int* d_status, int ctas_per_sm);
+gdf_error xjoin_build(const void* build_pairs, const unsigned long long* build_counts, unsigned nlocal, bool side, void** handle);
+gdf_error xjoin_probe(void* handle, const void* probe_pairs, const unsigned long long* probe_counts, gdf_column* out_l,
+                      gdf_column* out_r);
+gdf_error xjoin_count_dev(const gdf_column* key, unsigned ranks, unsigned nlocal, unsigned long long* d_counts);
+gdf_error xjoin_plan_dev(const unsigned long long* d_all, unsigned ranks, unsigned nlocal, unsigned rank, unsigned long long cap_build,
+                         unsigned long long cap_probe, unsigned long long* d_off_build, unsigned long long* d_off_probe,
+                         int* d_status);
 gdf_error xjoin_local(const void* probe_pairs, const unsigned long long* probe_counts, const void* build_pairs,
                       const unsigned long long* build_counts, unsigned nlocal, gdf_column* out_l, gdf_column* out_r);
 
@@ -714,7 +721,43 @@ extern "C" gdf_error gdfx_xjoin_scatter(gdf_column* key, int32_t id_base, int ra
   B200_REQUIRE(key->size < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
   B200_REQUIRE(ranks >= 1 && nlocal >= 1, GDF_INVALID_API_CALL);
   if (key->size == 0) return GDF_SUCCESS;
-  return xjoin_scatter(key, id_base, (unsigned)ranks, (unsigned)nlocal, dst_pairs, dst_offsets);
+  return xjoin_scatter(key, id_base, (unsigned)ranks, (unsigned)nlocal, dst_pairs, dst_offsets, nullptr, 0);
+}
+// the local join in two stages: tables are filled on a private stream while the probe side is still being exchanged
+extern "C" gdf_error gdfx_xjoin_build(const void* build_pairs, const unsigned long long* build_counts, int nlocal, int overlap,
+                                      void** handle) {
+  B200_REQUIRE(build_pairs && build_counts && handle, GDF_DATASET_EMPTY);
+  B200_REQUIRE(nlocal >= 1, GDF_INVALID_API_CALL);
+  return xjoin_build(build_pairs, build_counts, (unsigned)nlocal, overlap != 0, handle);
+}
+extern "C" gdf_error gdfx_xjoin_probe(void* handle, const void* probe_pairs, const unsigned long long* probe_counts,
+                                      gdf_column* out_l, gdf_column* out_r) {
+  B200_REQUIRE(handle && probe_pairs && probe_counts && out_l && out_r, GDF_DATASET_EMPTY);
+  return xjoin_probe(handle, probe_pairs, probe_counts, out_l, out_r);
+}
+// asynchronous variants: no host synchronisation anywhere (include/gdf_b200_ext.h)
+extern "C" gdf_error gdfx_xjoin_count_dev(gdf_column* key, int ranks, int nlocal, unsigned long long* d_counts) {
+  B200_REQUIRE(key != nullptr && d_counts != nullptr, GDF_DATASET_EMPTY);
+  B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
+  B200_REQUIRE(ranks >= 1 && nlocal >= 1, GDF_INVALID_API_CALL);
+  return xjoin_count_dev(key, (unsigned)ranks, (unsigned)nlocal, d_counts);
+}
+extern "C" gdf_error gdfx_xjoin_plan_dev(const unsigned long long* d_all, int ranks, int nlocal, int rank, unsigned long long cap_build,
+                                         unsigned long long cap_probe, unsigned long long* d_off_build,
+                                         unsigned long long* d_off_probe, int* d_status) {
+  B200_REQUIRE(d_all && d_off_build && d_off_probe && d_status, GDF_DATASET_EMPTY);
+  B200_REQUIRE(ranks >= 1 && nlocal >= 1 && rank >= 0, GDF_INVALID_API_CALL);
+  return xjoin_plan_dev(d_all, (unsigned)ranks, (unsigned)nlocal, (unsigned)rank, cap_build, cap_probe, d_off_build, d_off_probe,
+                        d_status);
+}
+extern "C" gdf_error gdfx_xjoin_scatter_dev(gdf_column* key, int32_t id_base, int ranks, int nlocal, void* const* dst_pairs,
+                                            const unsigned long long* d_offsets, const int* d_status, int ctas_per_sm) {
+  B200_REQUIRE(key && dst_pairs && d_offsets && d_status, GDF_DATASET_EMPTY);
+  B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
+  B200_REQUIRE(key->size < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
+  B200_REQUIRE(ranks >= 1 && nlocal >= 1, GDF_INVALID_API_CALL);
+  if (key->size == 0) return GDF_SUCCESS;
+  return xjoin_scatter(key, id_base, (unsigned)ranks, (unsigned)nlocal, dst_pairs, d_offsets, d_status, ctas_per_sm);
 }
 extern "C" gdf_error gdfx_xjoin_local(const void* probe_pairs, const unsigned long long* probe_counts, const void* build_pairs,
                                       const unsigned long long* build_counts, int nlocal, gdf_column* out_l, gdf_column* out_r) {

@@ -100,7 +100,7 @@ struct PartGeom {
 };
 
 // ---- pass 1: per-partition row counts.  Shared-memory 32-bit atomics are the cheapest primitive on
-// B200 for this (~2900 Gop/s measured, profiles/r01_microbench.txt; match.any-based ranking measured
+// B200 for this (~2900 Gop/s measured, profiles/r02_microbench.txt; match.any-based ranking measured
 // 20x slower), so the CTA histogram is plain atomicAdd on shared counters. ----
 // COMPACT (join_compact.cuh): rows whose 64-bit key has a non-zero high word cannot match a 32-bit build side and
 // are counted like NULL-key rows.  hi_or (if not null) receives the OR of the high words of all valid keys - the
@@ -358,6 +358,7 @@ struct PeerPairs {
   uint2* base[kMaxPeers];
   unsigned on;      // 0: everything goes to out_pairs
   unsigned shift;   // destination rank = bin >> shift  (shift = log2(nlocal))
+  const int* status;  // asynchronous exchange: device flags written by xjoin_plan_kernel; non-zero = write nothing
 };
 
 template <typename KT, bool KEEP_NULLS>
@@ -367,6 +368,8 @@ part_scatter32_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restr
                       const int32_t* __restrict__ payload, int32_t id_base, const PeerPairs peer) {
   extern __shared__ __align__(16) unsigned char scatter32_smem[];
   Scatter32Smem& sm = *reinterpret_cast<Scatter32Smem*>(scatter32_smem);
+  if (peer.status != nullptr && (peer.status[0] | peer.status[1]) != 0) return;  // the device-side plan said "do not write"
+
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   const size_t tiles = (n + kS32Tile - 1) / kS32Tile;
   for (unsigned p = threadIdx.x; p < 2 * kMaxParts; p += kS32Threads) (&sm.hist[0][0])[p] = 0;
@@ -1108,6 +1111,7 @@ gdf_error partition_hist(const gdf_column* col, PartGeom g, unsigned long long* 
                                                                     reinterpret_cast<unsigned*>(d_totals + g.nparts));
   }
   B200_CHECK_LAST();
+  if (h_totals == nullptr) return GDF_SUCCESS;  // device-only caller (asynchronous exchange): no read-back, no host sync
   unsigned long long h_all[kMaxParts + 1];
   B200_CUDA_TRY(cudaMemcpy(h_all, d_totals, (g.nparts + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   for (unsigned p = 0; p < g.nparts; ++p) h_totals[p] = h_all[p];
@@ -1118,22 +1122,29 @@ gdf_error partition_hist(const gdf_column* col, PartGeom g, unsigned long long* 
 template <typename KT, bool KEEP_NULLS>
 gdf_error partition_scatter32(const gdf_column* col, PartGeom g, const unsigned long long* h_cursors,
                               unsigned long long* d_cursors, uint2* out_pairs, const int32_t* payload, int32_t id_base,
-                              const PeerPairs* peer_dst = nullptr) {
+                              const PeerPairs* peer_dst = nullptr, bool cursors_on_device = false, int ctas_per_sm = 0) {
   PeerPairs peer;
   peer.on = 0;
   peer.shift = 0;
+  peer.status = nullptr;
   for (int r = 0; r < kMaxPeers; ++r) peer.base[r] = nullptr;
   if (peer_dst) peer = *peer_dst;
   const KT* keys = static_cast<const KT*>(col->data);
   const size_t n = col->size;
-  B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  if (cursors_on_device)  // asynchronous exchange: the plan lives on the device, nothing here waits for the GPU
+    B200_CUDA_TRY(cudaMemcpyAsync(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, 0));
+  else
+    B200_CUDA_TRY(cudaMemcpy(d_cursors, h_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
   auto kern = part_scatter32_kernel<KT, KEEP_NULLS>;
   const size_t smem_bytes = sizeof(Scatter32Smem);
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int per_sm = 1;
   B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kS32Threads, smem_bytes));
   const size_t tiles = (n + kS32Tile - 1) / kS32Tile;
-  const size_t cap = (size_t)sm_count() * (size_t)(per_sm > 0 ? per_sm : 1);  // exactly one resident wave
+  // exactly one resident wave; a caller that runs another kernel beside this one (the multi-GPU layer fills its hash
+  // tables while the probe side crosses NVLink) asks for fewer CTAs per SM, which leaves registers for the neighbour
+  if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
+  const size_t cap = (size_t)sm_count() * (size_t)(per_sm > 0 ? per_sm : 1);
   const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
   {
     B200_TIMED("join_part_scatter");
@@ -1284,52 +1295,88 @@ gdf_error launch_probe32_unique(const Pairs32& pr, PartGeom g, const Tables32& t
   return GDF_SUCCESS;
 }
 
+// Table geometry of the compact path, passed to the device BY VALUE (3 KB of kernel parameters): no host-to-device copy,
+// so nothing synchronises and the stage can run on any stream.
+struct TableMeta {
+  unsigned long long off[kMaxParts];
+  unsigned mask[kMaxParts];
+  unsigned n;
+};
+__global__ void table_meta_kernel(const TableMeta m, unsigned long long* __restrict__ d_toffset, unsigned* __restrict__ d_tmask) {
+  const unsigned p = threadIdx.x;
+  if (p < m.n) {
+    d_toffset[p] = m.off[p];
+    d_tmask[p] = m.mask[p];
+  }
+}
+
+// Stage 1 of the compact join: size, initialise and fill the per-partition tables, all on stream `s` (the legacy stream
+// for a single-GPU join; a private stream when the multi-GPU layer overlaps it with the probe side's exchange).
+gdf_error compact_build(PartGeom g, const Pairs32& bp, const unsigned long long* h_btot, unsigned long long* d_toffset,
+                        unsigned* d_tmask, int* d_flags, Scratch& table, Tables32* t_out, cudaStream_t s) {
+  TableMeta meta;
+  unsigned long long total_slots = 0;
+  for (unsigned p = 0; p < g.nparts; ++p) {  // load factor <= 0.5, whole buckets
+    unsigned slots = pow2_at_least(h_btot[p] ? 2 * h_btot[p] : 4);
+    if (slots < 4) slots = 4;
+    meta.off[p] = total_slots;
+    meta.mask[p] = slots - 1;
+    total_slots += slots;
+  }
+  meta.n = g.nparts;
+  table_meta_kernel<<<1, kMaxParts, 0, s>>>(meta, d_toffset, d_tmask);
+  B200_CHECK_LAST();
+  B200_CUDA_TRY(table.alloc(total_slots * sizeof(unsigned long long)));
+  const Tables32 t{table.as<unsigned long long>(), d_toffset, d_tmask};
+  *t_out = t;
+  // ONE memset + ONE build launch: filling the tables a few partitions at a time (so that the EMPTY pattern is still in
+  // L2 when the inserts arrive) measured slower - 32 rounds of 48 MB: 3.70 ms against 3.17 ms, the gaps and tails of 64
+  // small launches outweigh the L2 hits (profiles/r02_notes.md; lab knob B200_BUILD_ROUND_MB).
+  const unsigned long long kRoundSlots = ((unsigned long long)lab_knob("B200_BUILD_ROUND_MB", 1 << 20) << 20) / sizeof(unsigned long long);
+  unsigned long long pair_lo = 0;
+  for (unsigned p = 0; p < g.nparts;) {
+    unsigned q = p;
+    unsigned long long slots = 0, pairs = 0;
+    do {
+      slots += (unsigned long long)meta.mask[q] + 1;
+      pairs += h_btot[q];
+      ++q;
+    } while (q < g.nparts && slots + meta.mask[q] + 1 <= kRoundSlots);
+    B200_CUDA_TRY(cudaMemsetAsync(t.slots + meta.off[p], 0xff, slots * sizeof(unsigned long long), s));
+    if (pairs) {
+      const Pairs32 part{bp.pairs + pair_lo, (size_t)pairs};
+      build32_kernel<<<(unsigned)((pairs + kB32Tile - 1) / kB32Tile), kB32Threads, 0, s>>>(part, g, t, d_flags);
+      B200_CHECK_LAST();
+    }
+    pair_lo += pairs;
+    p = q;
+  }
+  return GDF_SUCCESS;
+}
+
+gdf_error compact_probe(int kind, bool flip, PartGeom g, const Tables32& t, const Pairs32& pp, size_t build_rows,
+                        unsigned long long* d_cursor, int* d_flags, const unsigned long long* d_pstart, gdf_column* out_l,
+                        gdf_column* out_r);
+
 // d_pstart: device array [nparts + 1], first pair of every partition in pp.pairs (last entry = pp.n)
 gdf_error run_compact(int kind, bool flip, PartGeom g, const Pairs32& bp, const Pairs32& pp, const unsigned long long* h_btot,
                       size_t build_rows, unsigned long long* d_toffset, unsigned* d_tmask, unsigned long long* d_cursor,
                       int* d_flags, const unsigned long long* d_pstart, gdf_column* out_l, gdf_column* out_r) {
-  const bool left_like = kind != JOIN_INNER;
-  unsigned long long h_toffset[kMaxParts], total_slots = 0;
-  unsigned h_tmask[kMaxParts];
-  for (unsigned p = 0; p < g.nparts; ++p) {  // load factor <= 0.5, whole buckets
-    unsigned slots = pow2_at_least(h_btot[p] ? 2 * h_btot[p] : 4);
-    if (slots < 4) slots = 4;
-    h_toffset[p] = total_slots;
-    h_tmask[p] = slots - 1;
-    total_slots += slots;
-  }
-  B200_CUDA_TRY(cudaMemcpy(d_toffset, h_toffset, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  B200_CUDA_TRY(cudaMemcpy(d_tmask, h_tmask, g.nparts * sizeof(unsigned), cudaMemcpyHostToDevice));
   Scratch table;
-  B200_CUDA_TRY(table.alloc(total_slots * sizeof(unsigned long long)));
-  Tables32 t{table.as<unsigned long long>(), d_toffset, d_tmask};
+  Tables32 t{nullptr, nullptr, nullptr};
   {
-    // Tables can be initialised and filled a few partitions at a time (lab knob B200_BUILD_ROUND_MB) so that the EMPTY
-    // pattern written by the memset is still in L2 when the inserts arrive (ncu, one memset + one build launch: 2.9 GB
-    // read + 1.6 GB written by the build kernel, 2.85 ms).
     B200_TIMED("join_part_build");
-    // measured (profiles/r02_notes.md): 32 rounds of 48 MB cost 3.70 ms against 3.17 ms for ONE memset + ONE build launch -
-    // the launch gaps and tails of 64 small launches outweigh the L2 hits - so the default is a single round
-    const unsigned long long kRoundSlots = ((unsigned long long)lab_knob("B200_BUILD_ROUND_MB", 1 << 20) << 20) / sizeof(unsigned long long);
-    unsigned long long pair_lo = 0;
-    for (unsigned p = 0; p < g.nparts;) {
-      unsigned q = p;
-      unsigned long long slots = 0, pairs = 0;
-      do {
-        slots += (unsigned long long)h_tmask[q] + 1;
-        pairs += h_btot[q];
-        ++q;
-      } while (q < g.nparts && slots + h_tmask[q] + 1 <= kRoundSlots);
-      B200_CUDA_TRY(cudaMemsetAsync(t.slots + h_toffset[p], 0xff, slots * sizeof(unsigned long long), 0));
-      if (pairs) {
-        const Pairs32 part{bp.pairs + pair_lo, (size_t)pairs};
-        build32_kernel<<<(unsigned)((pairs + kB32Tile - 1) / kB32Tile), kB32Threads>>>(part, g, t, d_flags);
-        B200_CHECK_LAST();
-      }
-      pair_lo += pairs;
-      p = q;
-    }
+    const gdf_error e = compact_build(g, bp, h_btot, d_toffset, d_tmask, d_flags, table, &t, 0);
+    if (e != GDF_SUCCESS) return e;
   }
+  return compact_probe(kind, flip, g, t, pp, build_rows, d_cursor, d_flags, d_pstart, out_l, out_r);
+}
+
+// Stage 2: probe + output (legacy stream).  `t` was filled by compact_build; the caller has ordered this stream after it.
+gdf_error compact_probe(int kind, bool flip, PartGeom g, const Tables32& t, const Pairs32& pp, size_t build_rows,
+                        unsigned long long* d_cursor, int* d_flags, const unsigned long long* d_pstart, gdf_column* out_l,
+                        gdf_column* out_r) {
+  const bool left_like = kind != JOIN_INNER;
   int h_flags[2] = {0, 0};
   B200_CUDA_TRY(cudaMemcpy(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
   const bool unique = h_flags[0] == 0;
@@ -1402,7 +1449,7 @@ gdf_error run_compact(int kind, bool flip, PartGeom g, const Pairs32& bp, const 
           const int fsmem = kFixCap * (int)(sizeof(unsigned long long) + 3 * sizeof(unsigned));
           cudaFuncSetAttribute(fixup_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem);
           fixup_plan_kernel<<<1, kFixThreads, fsmem>>>(out.hole_start, out.hole_len, 2 * warps, d_cursor, plan.as<FixPlan>());
-          fixup_move_kernel<<<sm_count() * 2, 256>>>(plan.as<FixPlan>(), op, ob);
+          fixup_move_kernel<<<sm_count() * 32, 256>>>(plan.as<FixPlan>(), op, ob);  // two dependent binary searches per pair: latency is hidden by threads, not by a loop
           if (cudaPeekAtLastError() != cudaSuccess) e = GDF_CUDA_ERROR;
         }
         if (e == GDF_SUCCESS) e = read_u64(&plan.as<FixPlan>()->found, &found);
@@ -1757,62 +1804,221 @@ gdf_error xjoin_count(const gdf_column* key, unsigned ranks, unsigned nlocal, un
 // dst_pairs[r] = rank r's pair buffer as mapped on THIS device; h_offsets[r * nlocal + p] = position inside it of this
 // rank's first pair of local partition p.  Rows whose key does not fit 32 bits are dropped (they cannot match).
 gdf_error xjoin_scatter(const gdf_column* key, int32_t id_base, unsigned ranks, unsigned nlocal, void* const* dst_pairs,
-                        const unsigned long long* h_offsets) {
+                        const unsigned long long* h_offsets, const int* d_status /* non-null: h_offsets is a DEVICE array */,
+                        int ctas_per_sm) {
   B200_REQUIRE(ranks >= 1 && ranks <= (unsigned)kMaxPeers && nlocal >= 1 && (nlocal & (nlocal - 1)) == 0 &&
                    ranks * nlocal <= kMaxParts, GDF_INVALID_API_CALL);
   const PartGeom g = combined_geom(ranks, nlocal);
   PeerPairs peer;
   peer.on = 1;
   peer.shift = 32 - g.shift;
+  peer.status = d_status;
   for (int r = 0; r < kMaxPeers; ++r) peer.base[r] = r < (int)ranks ? static_cast<uint2*>(dst_pairs[r]) : nullptr;
   Scratch small;
   B200_CUDA_TRY(small.alloc((size_t)g.nparts * sizeof(unsigned long long)));
+  const bool dev = d_status != nullptr;  // offsets are a device array (asynchronous exchange)
   switch (key->dtype) {
     case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
-      return partition_scatter32<uint64_t, false>(key, g, h_offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer);
+      return partition_scatter32<uint64_t, false>(key, g, h_offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer, dev, ctas_per_sm);
     case GDF_INT32: case GDF_DATE32:
-      return partition_scatter32<uint32_t, false>(key, g, h_offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer);
+      return partition_scatter32<uint32_t, false>(key, g, h_offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer, dev, ctas_per_sm);
     default: return GDF_UNSUPPORTED_DTYPE;
   }
 }
 
+// ---- asynchronous variant of the exchange: counts and plan stay on the device, the host never waits between the
+// histogram and the scatter (round 2, first version: ~1.2 of 5.5 ms at 8 GPUs were host round trips) ----
+// d_counts[ranks * nlocal + 1]: rows per bin, then the OR of the keys' high words (as a 64-bit cell).
+gdf_error xjoin_count_dev(const gdf_column* key, unsigned ranks, unsigned nlocal, unsigned long long* d_counts) {
+  B200_REQUIRE(ranks >= 1 && ranks <= (unsigned)kMaxPeers && nlocal >= 1 && (nlocal & (nlocal - 1)) == 0 &&
+                   ranks * nlocal <= kMaxParts, GDF_INVALID_API_CALL);
+  const PartGeom g = combined_geom(ranks, nlocal);
+  if (key->size == 0) {
+    B200_CUDA_TRY(cudaMemsetAsync(d_counts, 0, ((size_t)g.nparts + 1) * sizeof(unsigned long long), 0));
+    return GDF_SUCCESS;
+  }
+  switch (key->dtype) {
+    case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
+      return partition_hist<uint64_t, false, true>(key, g, d_counts, nullptr);
+    case GDF_INT32: case GDF_DATE32:
+      return partition_hist<uint32_t, false, true>(key, g, d_counts, nullptr);
+    default: return GDF_UNSUPPORTED_DTYPE;
+  }
+}
+
+// all[s * stride + side * (bins + 1) + b] = pairs rank s sends to bin b of `side` (0 build, 1 probe), cell [bins] = OR of
+// the side's high key words.  One CTA, one thread per bin.  Receiver d lays its buffer out partition-major and, inside a
+// partition, in sender order (dist.plan_fused_exchange is the host statement of the same arithmetic):
+//   off[side][b]   where THIS rank's pairs of bin b start inside the destination's buffer
+//   status[0] = 1  a build key somewhere does not fit 32 bits (compact exchange not applicable)
+//   status[1] = 1  some rank would receive more pairs than its buffer holds (cap_build / cap_probe)
+__global__ void xjoin_plan_kernel(const unsigned long long* __restrict__ all, unsigned ranks, unsigned nlocal, unsigned rank,
+                                  unsigned long long cap_build, unsigned long long cap_probe,
+                                  unsigned long long* __restrict__ off_build, unsigned long long* __restrict__ off_probe,
+                                  int* __restrict__ status) {
+  __shared__ unsigned long long tot[kMaxParts];
+  const unsigned bins = ranks * nlocal, stride = 2 * (bins + 1);
+  const unsigned b = threadIdx.x;
+  if (b == 0) {
+    unsigned long long wide = 0;
+    for (unsigned s = 0; s < ranks; ++s) wide |= all[(size_t)s * stride + bins];
+    if (wide) status[0] = 1;
+  }
+  for (unsigned side = 0; side < 2; ++side) {
+    unsigned long long before_me = 0, total = 0;
+    if (b < bins)
+      for (unsigned s = 0; s < ranks; ++s) {
+        const unsigned long long c = all[(size_t)s * stride + side * (bins + 1) + b];
+        if (s < rank) before_me += c;
+        total += c;
+      }
+    __syncthreads();  // the previous side's reads of tot[] are done
+    if (b < bins) tot[b] = total;
+    __syncthreads();
+    if (b < bins) {
+      const unsigned d = b / nlocal;
+      unsigned long long start = 0;
+      for (unsigned q = d * nlocal; q < b; ++q) start += tot[q];
+      (side ? off_probe : off_build)[b] = start + before_me;
+      if (b % nlocal == nlocal - 1 && start + total > (side ? cap_probe : cap_build)) status[1] = 1;
+    }
+  }
+}
+
+gdf_error xjoin_plan_dev(const unsigned long long* d_all, unsigned ranks, unsigned nlocal, unsigned rank, unsigned long long cap_build,
+                         unsigned long long cap_probe, unsigned long long* d_off_build, unsigned long long* d_off_probe,
+                         int* d_status) {
+  B200_REQUIRE(ranks >= 1 && ranks <= (unsigned)kMaxPeers && nlocal >= 1 && ranks * nlocal <= kMaxParts && rank < ranks,
+               GDF_INVALID_API_CALL);
+  B200_CUDA_TRY(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), 0));
+  xjoin_plan_kernel<<<1, kMaxParts>>>(d_all, ranks, nlocal, rank, cap_build, cap_probe, d_off_build, d_off_probe, d_status);
+  B200_CHECK_LAST();
+  return GDF_SUCCESS;
+}
+
 // INNER join of partition-contiguous compact pairs (this rank's receive buffers): counts[p] = pairs of local partition p.
-gdf_error xjoin_local(const void* probe_pairs, const unsigned long long* probe_counts, const void* build_pairs,
-                      const unsigned long long* build_counts, unsigned nlocal, gdf_column* out_l, gdf_column* out_r) {
-  B200_REQUIRE(nlocal >= 1 && nlocal <= kMaxParts && (nlocal & (nlocal - 1)) == 0, GDF_INVALID_API_CALL);
+// Two stages so that the multi-GPU layer can fill the tables while the probe side is still crossing NVLink:
+//   xjoin_build  ordered after everything issued so far on the legacy stream, runs on a private non-blocking stream
+//                (side = true) or on the legacy stream itself, returns a handle
+//   xjoin_probe  makes the legacy stream wait for the build, probes, writes the outputs, releases the handle
+struct XJoinHandle {
+  Scratch small, table;
+  Tables32 t{nullptr, nullptr, nullptr};
   PartGeom g;
-  g.nparts = nlocal;
-  g.dest = 0;
-  g.nlocal = 0;
-  unsigned lg = 0;
-  while ((1u << lg) < nlocal) ++lg;
-  g.shift = 32 - lg;
-  unsigned long long h_pstart[kMaxParts + 1], build_rows = 0, probe_rows = 0, slots32 = 0;
+  unsigned long long build_rows = 0;
+  unsigned long long* d_cursor = nullptr;
+  int* d_flags = nullptr;
+  unsigned long long* d_pstart = nullptr;
+  cudaEvent_t done = nullptr;
+  bool side = false;
+};
+
+static cudaStream_t xjoin_side_stream() {
+  static cudaStream_t s = nullptr;
+  if (s == nullptr && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+  return s;
+}
+
+gdf_error xjoin_build(const void* build_pairs, const unsigned long long* build_counts, unsigned nlocal, bool side, void** handle) {
+  B200_REQUIRE(nlocal >= 1 && nlocal <= kMaxParts && (nlocal & (nlocal - 1)) == 0, GDF_INVALID_API_CALL);
+  *handle = nullptr;
+  unsigned long long build_rows = 0, slots32 = 0;
   for (unsigned p = 0; p < nlocal; ++p) {
-    h_pstart[p] = probe_rows;
-    probe_rows += probe_counts[p];
     build_rows += build_counts[p];
     B200_REQUIRE(build_counts[p] <= (1u << 22), GDF_COLUMN_SIZE_TOO_BIG);  // limits of the compact probe (run_partitioned)
     slots32 += pow2_at_least(build_counts[p] ? 2 * build_counts[p] : 4);
   }
-  h_pstart[nlocal] = probe_rows;
   B200_REQUIRE(slots32 < (1ull << 32) - 8, GDF_COLUMN_SIZE_TOO_BIG);
+  XJoinHandle* h = new XJoinHandle();
+  h->g.nparts = nlocal;
+  h->g.dest = 0;
+  h->g.nlocal = 0;
+  unsigned lg = 0;
+  while ((1u << lg) < nlocal) ++lg;
+  h->g.shift = 32 - lg;
+  h->build_rows = build_rows;
+  h->side = side;
+  // toffset[np] | cursor, flags (64 bytes) | pstart[np + 1] | tmask[np]
+  cudaError_t ce = h->small.alloc(((size_t)nlocal * 2 + 1) * sizeof(unsigned long long) + 64 + nlocal * sizeof(unsigned));
+  cudaStream_t s = 0;
+  if (ce == cudaSuccess && side) {
+    s = xjoin_side_stream();
+    if (s == nullptr) ce = cudaErrorUnknown;
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+    if (ce == cudaSuccess) {   // order the private stream after everything the caller has issued (the build side's exchange)
+      cudaEvent_t issued = nullptr;
+      ce = cudaEventCreateWithFlags(&issued, cudaEventDisableTiming);
+      if (ce == cudaSuccess) ce = cudaEventRecord(issued, 0);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, issued, 0);
+      if (issued) cudaEventDestroy(issued);
+    }
+  }
+  if (ce != cudaSuccess) {
+    delete h;
+    return GDF_CUDA_ERROR;
+  }
+  unsigned long long* d_toffset = h->small.as<unsigned long long>();
+  h->d_cursor = d_toffset + nlocal;
+  h->d_flags = reinterpret_cast<int*>(h->d_cursor + 1);
+  h->d_pstart = h->d_cursor + 8;
+  unsigned* d_tmask = reinterpret_cast<unsigned*>(h->d_pstart + nlocal + 1);
+  gdf_error e = GDF_SUCCESS;
+  if (cudaMemsetAsync(h->d_cursor, 0, 64, s) != cudaSuccess) e = GDF_CUDA_ERROR;
+  if (e == GDF_SUCCESS && build_rows) {
+    const Pairs32 bp{static_cast<const uint2*>(build_pairs), (size_t)build_rows};
+    if (side) {
+      e = compact_build(h->g, bp, build_counts, d_toffset, d_tmask, h->d_flags, h->table, &h->t, s);
+    } else {
+      B200_TIMED("join_part_build");
+      e = compact_build(h->g, bp, build_counts, d_toffset, d_tmask, h->d_flags, h->table, &h->t, s);
+    }
+  }
+  if (e == GDF_SUCCESS && side && cudaEventRecord(h->done, s) != cudaSuccess) e = GDF_CUDA_ERROR;
+  if (e != GDF_SUCCESS) {
+    if (side) cudaStreamSynchronize(s);   // nothing of the handle's memory may still be in use when it is released
+    if (h->done) cudaEventDestroy(h->done);
+    delete h;
+    return e;
+  }
+  *handle = h;
+  return GDF_SUCCESS;
+}
+
+gdf_error xjoin_probe(void* handle, const void* probe_pairs, const unsigned long long* probe_counts, gdf_column* out_l,
+                      gdf_column* out_r) {
+  XJoinHandle* h = static_cast<XJoinHandle*>(handle);
+  const unsigned nlocal = h->g.nparts;
+  unsigned long long h_pstart[kMaxParts + 1], probe_rows = 0;
+  for (unsigned p = 0; p < nlocal; ++p) {
+    h_pstart[p] = probe_rows;
+    probe_rows += probe_counts[p];
+  }
+  h_pstart[nlocal] = probe_rows;
+  gdf_error e = GDF_SUCCESS;
+  if (h->side && cudaStreamWaitEvent(0, h->done, 0) != cudaSuccess) e = GDF_CUDA_ERROR;
   view_indices(out_l, nullptr, 0);
   view_indices(out_r, nullptr, 0);
-  if (probe_rows == 0 || build_rows == 0) return GDF_SUCCESS;
-  Scratch small;  // toffset[np] | cursor, flags (64 bytes) | pstart[np + 1] | tmask[np]
-  B200_CUDA_TRY(small.alloc(((size_t)nlocal * 2 + 1) * sizeof(unsigned long long) + 64 + nlocal * sizeof(unsigned)));
-  unsigned long long* d_toffset = small.as<unsigned long long>();
-  unsigned long long* d_cursor = d_toffset + nlocal;
-  int* d_flags = reinterpret_cast<int*>(d_cursor + 1);
-  unsigned long long* d_pstart = d_cursor + 8;
-  unsigned* d_tmask = reinterpret_cast<unsigned*>(d_pstart + nlocal + 1);
-  B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 64, 0));
-  B200_CUDA_TRY(cudaMemcpy(d_pstart, h_pstart, (nlocal + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  const Pairs32 bp{static_cast<const uint2*>(build_pairs), (size_t)build_rows};
-  const Pairs32 pp{static_cast<const uint2*>(probe_pairs), (size_t)probe_rows};
-  return run_compact(JOIN_INNER, false, g, bp, pp, build_counts, (size_t)build_rows, d_toffset, d_tmask, d_cursor, d_flags,
-                     d_pstart, out_l, out_r);
+  if (e == GDF_SUCCESS && probe_rows != 0 && h->build_rows != 0) {
+    if (cudaMemcpy(h->d_pstart, h_pstart, (nlocal + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice) != cudaSuccess)
+      e = GDF_CUDA_ERROR;
+    const Pairs32 pp{static_cast<const uint2*>(probe_pairs), (size_t)probe_rows};
+    if (e == GDF_SUCCESS)
+      e = compact_probe(JOIN_INNER, false, h->g, h->t, pp, (size_t)h->build_rows, h->d_cursor, h->d_flags, h->d_pstart, out_l, out_r);
+  }
+  if (h->side) {
+    cudaStreamSynchronize(xjoin_side_stream());  // (already complete: the legacy stream waited for it)
+    cudaEventDestroy(h->done);
+  }
+  delete h;   // scratch goes back to the cache; every user of it was ordered on, or awaited by, the legacy stream
+  return e;
+}
+
+gdf_error xjoin_local(const void* probe_pairs, const unsigned long long* probe_counts, const void* build_pairs,
+                      const unsigned long long* build_counts, unsigned nlocal, gdf_column* out_l, gdf_column* out_r) {
+  void* h = nullptr;
+  const gdf_error e = xjoin_build(build_pairs, build_counts, nlocal, false, &h);
+  if (e != GDF_SUCCESS) return e;
+  return xjoin_probe(h, probe_pairs, probe_counts, out_l, out_r);
 }
 
 gdf_error partition_pairs(const gdf_column* key, int32_t id_base, unsigned num_partitions, void* out_keys,

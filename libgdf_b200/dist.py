@@ -143,13 +143,43 @@ class GdfOps(object):
         off = ffi.new("unsigned long long[]", [int(o) for o in offsets])
         lib.gdfx_xjoin_scatter(self.C.Column(keys).cdata, id_base, ranks, nlocal, dp, off)
 
+    def xjoin_count_dev(self, keys, ranks, nlocal, d_counts):
+        self.lib.gdfx_xjoin_count_dev(self.C.Column(keys).cdata, ranks, nlocal, self.ffi.cast("unsigned long long*", d_counts.data_ptr()))
+
+    def xjoin_plan_dev(self, d_all, ranks, nlocal, rank, cap_build, cap_probe, d_off_build, d_off_probe, d_status):
+        c = self.ffi.cast
+        self.lib.gdfx_xjoin_plan_dev(c("unsigned long long*", d_all.data_ptr()), ranks, nlocal, rank, cap_build, cap_probe,
+                                     c("unsigned long long*", d_off_build.data_ptr()), c("unsigned long long*", d_off_probe.data_ptr()),
+                                     c("int*", d_status.data_ptr()))
+
+    def xjoin_scatter_dev(self, keys, id_base, ranks, nlocal, dst_ptrs, d_offsets, d_status, ctas_per_sm=0):
+        ffi, lib = self.ffi, self.lib
+        dp = ffi.new("void*[]", [ffi.cast("void*", p) for p in dst_ptrs])
+        lib.gdfx_xjoin_scatter_dev(self.C.Column(keys).cdata, id_base, ranks, nlocal, dp,
+                                   ffi.cast("unsigned long long*", d_offsets.data_ptr()), ffi.cast("int*", d_status.data_ptr()),
+                                   ctas_per_sm)
+
+    def xjoin_build(self, build_ptr, build_counts, nlocal, overlap):
+        ffi, lib = self.ffi, self.lib
+        h = ffi.new("void**")
+        lib.gdfx_xjoin_build(ffi.cast("void*", build_ptr), ffi.new("unsigned long long[]", [int(c) for c in build_counts]), nlocal,
+                             1 if overlap else 0, h)
+        return h[0]
+
+    def xjoin_probe(self, handle, probe_ptr, probe_counts):
+        C, ffi, lib = self.C, self.ffi, self.lib
+        out_l, out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
+        lib.gdfx_xjoin_probe(handle, ffi.cast("void*", probe_ptr), ffi.new("unsigned long long[]", [int(c) for c in probe_counts]),
+                             out_l, out_r)
+        return C.library_owned_view(out_l), C.library_owned_view(out_r)
+
     def xjoin_local(self, probe_ptr, probe_counts, build_ptr, build_counts, nlocal):
         C, ffi, lib = self.C, self.ffi, self.lib
         out_l, out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
         lib.gdfx_xjoin_local(ffi.cast("void*", probe_ptr), ffi.new("unsigned long long[]", [int(c) for c in probe_counts]),
                              ffi.cast("void*", build_ptr), ffi.new("unsigned long long[]", [int(c) for c in build_counts]),
                              nlocal, out_l, out_r)
-        return C.library_owned_to_torch(out_l), C.library_owned_to_torch(out_r)
+        return C.library_owned_view(out_l), C.library_owned_view(out_r)
 
     def peer_alloc(self, nbytes):
         ffi, lib = self.ffi, self.lib
@@ -246,6 +276,12 @@ class PeerExchange(object):
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.slots = {}   # name -> {"cap", "itemsize", "mine": (kptr, iptr), "peers": ([kptr..], [iptr..])}
         self._flag = None
+        self.one_pass = True                  # fused_inner_join (one partition pass per side) before the two-pass path
+        self.async_plan = True                # steady state keeps counts / plan on the device (no host round trips)
+        self._async_state = {}
+        self.overlap_build = True             # fill the hash tables on a second stream during the probe side's exchange
+        self.scatter_ctas_per_sm = 2          # ... whose scatter then leaves a third of every SM to the table build
+        self.rows_per_partition = 1 << 20     # build rows per receiver-local partition of the one-pass exchange
 
     @staticmethod
     def available(ops, group=None):
@@ -333,18 +369,31 @@ class PeerExchange(object):
         self.slots[name] = slot
         return slot
 
-    def fused_inner_join(self, probe_keys, build_keys, probe_offset, build_offset, timings=None):
+    def fused_inner_join(self, probe_keys, build_keys, probe_offset, build_offset, timings=None, global_build_rows=None):
         """INNER join with ONE partition pass per side: every rank histograms both sides with the combined
         (destination rank x receiver-local partition) geometry, ONE all_gather carries both count matrices, ONE
         scatter per side stores compact pairs into the peers' partition-contiguous buffers over NVLink, and the
         receiver joins what it got without partitioning again.  Returns None when the compact form does not apply
-        (a build key wider than 32 bits, a partition too large): the caller then takes the two-pass path."""
+        (a build key wider than 32 bits, a partition too large): the caller then takes the two-pass path.
+
+        Steady state (receive buffers exist) is ASYNCHRONOUS: counts, the all-gathered matrix and the write offsets stay
+        on the device (gdfx_xjoin_count_dev / _plan_dev / _scatter_dev), a side stream copies the matrix to pinned host
+        memory while the scatters run, and the host only reads it when it needs the per-partition totals for the local
+        join.  The device-side plan raises a flag instead of writing when a buffer would overflow or a build key is wide;
+        the host sees the flag afterwards and falls back to the synchronous route, which also (re)allocates buffers."""
         world, rank, dev = self.world, self.rank, probe_keys.device
         ev = _Stamps(timings, dev)
-        sizes = torch.tensor([build_keys.numel()], dtype=torch.int64, device=dev)
-        dist.all_reduce(sizes, group=self.group)
-        nlocal = fused_nlocal(int(sizes.item()), world)
+        if global_build_rows is None:       # one collective + host read; callers that know their table sizes pass them
+            sizes = torch.tensor([build_keys.numel()], dtype=torch.int64, device=dev)
+            dist.all_reduce(sizes, group=self.group)
+            global_build_rows = int(sizes.item())
+        nlocal = fused_nlocal(global_build_rows, world, self.rows_per_partition)
         bins = world * nlocal
+        sb, sp = self.slots.get("xbuild"), self.slots.get("xprobe")
+        if self.async_plan and sb and sp and sb.get("pairs") and sp.get("pairs"):
+            out = self._fused_async(probe_keys, build_keys, probe_offset, build_offset, nlocal, sb, sp, ev)
+            if out is not False:
+                return out
         cb, hi_b = self.ops.xjoin_count(build_keys, world, nlocal)
         cp, _ = self.ops.xjoin_count(probe_keys, world, nlocal)
         mine = torch.tensor(cb + cp + [hi_b], dtype=torch.int64, device=dev)
@@ -366,6 +415,58 @@ class PeerExchange(object):
         dist.all_reduce(self._flag, group=self.group)                 # stream-ordered: every rank's stores have landed
         ev.mark("partition+exchange")
         out = self.ops.xjoin_local(sp["mine"][0], tot_p, sb["mine"][0], tot_b, nlocal)
+        ev.mark("local_join")
+        return out
+
+    def _fused_async(self, probe_keys, build_keys, probe_offset, build_offset, nlocal, sb, sp, ev):
+        """The steady-state route of fused_inner_join.  Returns False when the synchronous route has to run instead
+        (a receive buffer is too small), None / (left, right) otherwise."""
+        world, rank, dev = self.world, self.rank, probe_keys.device
+        bins = world * nlocal
+        stride = 2 * (bins + 1)                      # per rank: build bins | build hi_or | probe bins | probe hi_or
+        st = self._async_state.get(stride)
+        if st is None:
+            st = {"mine": torch.zeros(stride, dtype=torch.int64, device=dev),
+                  "all": torch.zeros(world * stride, dtype=torch.int64, device=dev),
+                  "off": torch.zeros(2 * bins, dtype=torch.int64, device=dev),
+                  "status": torch.zeros(2, dtype=torch.int32, device=dev),
+                  "pin": torch.zeros(world * stride + 2, dtype=torch.int64).pin_memory(),
+                  "side": torch.cuda.Stream(device=dev)}
+            self._async_state[stride] = st
+        mine, allc, off, status = st["mine"], st["all"], st["off"], st["status"]
+        self.ops.xjoin_count_dev(build_keys, world, nlocal, mine[:bins + 1])
+        self.ops.xjoin_count_dev(probe_keys, world, nlocal, mine[bins + 1:])
+        dist.all_gather_into_tensor(allc, mine, group=self.group)     # also: everybody is done with the previous buffers
+        self.ops.xjoin_plan_dev(allc, world, nlocal, rank, sb["cap"], sp["cap"], off[:bins], off[bins:], status)
+        gathered = torch.cuda.Event()
+        gathered.record()
+        with torch.cuda.stream(st["side"]):         # matrix + flags to pinned memory while the scatters run
+            st["side"].wait_event(gathered)
+            st["pin"][:world * stride].copy_(allc, non_blocking=True)
+            st["pin"][world * stride:].copy_(status.to(torch.int64), non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record()
+        ev.mark("count+plan")
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ops.xjoin_scatter_dev(build_keys, build_offset, world, nlocal, sb["peers"][0], off[:bins], status)
+        dist.all_reduce(self._flag, group=self.group)                 # stream-ordered: every rank's BUILD pairs have landed
+        copied.synchronize()                                          # long done: the copy only waited for the all_gather
+        M = st["pin"][:world * stride].view(world, stride).numpy()
+        wide, overflow = int(st["pin"][world * stride]), int(st["pin"][world * stride + 1])
+        if wide or overflow:                                          # nothing was / will be written (the scatters check the flags)
+            return None if wide else False                            # two-pass path / synchronous route that grows the buffers
+        tot_b = M[:, rank * nlocal:(rank + 1) * nlocal].sum(0)
+        tot_p = M[:, bins + 1 + rank * nlocal:bins + 1 + (rank + 1) * nlocal].sum(0)
+        if int(tot_b.max()) > (1 << 22):
+            return None
+        # tables are filled on a private stream while the probe side crosses NVLink on this one
+        handle = self.ops.xjoin_build(sb["mine"][0], tot_b.tolist(), nlocal, self.overlap_build)
+        self.ops.xjoin_scatter_dev(probe_keys, probe_offset, world, nlocal, sp["peers"][0], off[bins:], status,
+                                   self.scatter_ctas_per_sm if self.overlap_build else 0)
+        dist.all_reduce(self._flag, group=self.group)                 # every rank's PROBE pairs have landed
+        ev.mark("partition+exchange")
+        out = self.ops.xjoin_probe(handle, sp["mine"][0], tot_p.tolist())
         ev.mark("local_join")
         return out
 
@@ -396,15 +497,13 @@ def plan_fused_exchange(counts, world, nlocal, rank):
         part_totals[p]           pairs of local partition p this rank receives (all senders)
         recv_rows[d]             total pairs rank d receives (buffer sizing)
     Pure arithmetic on the gathered count matrix: every rank computes the same plan (tests/test_dist_cpu.py)."""
-    offsets, recv_rows = [0] * (world * nlocal), [0] * world
-    for d in range(world):
-        run = 0
-        for p in range(nlocal):
-            b = d * nlocal + p
-            offsets[b] = run + sum(counts[s][b] for s in range(rank))
-            run += sum(counts[s][b] for s in range(world))
-        recv_rows[d] = run
-    part_totals = [sum(counts[s][rank * nlocal + p] for s in range(world)) for p in range(nlocal)]
+    c = np.asarray(counts, dtype=np.int64).reshape(world, world * nlocal)
+    totals = c.sum(0)                                             # pairs of every bin, all senders
+    before_me = c[:rank].sum(0)                                   # ... of the senders ranked before this one
+    bin_start = (np.cumsum(totals.reshape(world, nlocal), 1) - totals.reshape(world, nlocal)).reshape(-1)   # inside its destination
+    offsets = (bin_start + before_me).tolist()
+    recv_rows = totals.reshape(world, nlocal).sum(1).tolist()
+    part_totals = totals[rank * nlocal:(rank + 1) * nlocal].tolist()
     return offsets, part_totals, recv_rows
 
 
@@ -431,11 +530,14 @@ def shard_bounds(total_rows, world, rank):
 # ------------------------------------------------------------------------------------------------
 # distributed operators
 # ------------------------------------------------------------------------------------------------
-def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops, group=None, timings=None, peer=None):
+def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops, group=None, timings=None, peer=None,
+                     global_rows=None):
     """Hash join of block-distributed key columns.
 
     left_keys / right_keys   this rank's shard of the (single, integer) key column
     left_offset/right_offset global row index of the shard's first row
+    global_rows              optional (total left rows, total right rows) over all ranks: a caller that knows its table
+                             sizes saves the collective + host read that would otherwise establish them
     Returns (left_idx, right_idx): int32 GLOBAL row ids of this rank's share of the result (-1 =
     no partner, LEFT join).  The union over ranks is the join of the full tables (pair order
     unspecified, as in the reference).
@@ -448,11 +550,13 @@ def distributed_join(kind, left_keys, right_keys, left_offset, right_offset, ops
     fn = ops.inner_join if kind == "inner" else ops.left_join
     if peer is not None and kind == "inner" and getattr(peer, "one_pass", True):
         # one partition pass per side: the build side is the smaller table (gdf_inner_join's rule, joining.h:59-67)
-        sizes = torch.tensor([left_keys.numel(), right_keys.numel()], dtype=torch.int64, device=dev)
-        dist.all_reduce(sizes, group=group)
-        flip = int(sizes[1].item()) > int(sizes[0].item())
-        out = (peer.fused_inner_join(right_keys, left_keys, right_offset, left_offset, timings) if flip
-               else peer.fused_inner_join(left_keys, right_keys, left_offset, right_offset, timings))
+        if global_rows is None:
+            sizes = torch.tensor([left_keys.numel(), right_keys.numel()], dtype=torch.int64, device=dev)
+            dist.all_reduce(sizes, group=group)
+            global_rows = tuple(int(x) for x in sizes.tolist())
+        flip = global_rows[1] > global_rows[0]
+        out = (peer.fused_inner_join(right_keys, left_keys, right_offset, left_offset, timings, global_rows[0]) if flip
+               else peer.fused_inner_join(left_keys, right_keys, left_offset, right_offset, timings, global_rows[1]))
         if out is not None:
             return (out[1], out[0]) if flip else out
     if peer is not None:   # two-pass path: partition + exchange over NVLink peer memory, then the local partitioned join

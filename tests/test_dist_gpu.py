@@ -213,3 +213,70 @@ def test_one_pass_fused_exchange_reports_wide_keys():
     keys = torch.tensor([1, 2, (1 << 40) + 3, 4], dtype=torch.int64, device="cuda")
     counts, hi = ops.xjoin_count(keys, 2, 4)
     assert hi != 0 and sum(counts) == 3          # the wide key is counted nowhere, exactly as the scatter drops it
+
+
+@pytest.mark.parametrize("world,nlocal", [(2, 8), (3, 4), (8, 32)])
+def test_device_side_exchange_plan_equals_host_plan(world, nlocal):
+    """The asynchronous route of the one-pass exchange keeps counts and plan on the device (gdfx_xjoin_count_dev /
+    _plan_dev / _scatter_dev).  Same counts, same offsets as the host plan, same bytes in the receive buffers; and the
+    status flags stop the scatter (nothing written) when a buffer is too small or a build key is wide."""
+    ops = D.GdfOps()
+    P, B = 300_007, 40_000
+    probe = np.random.randint(0, 2 * B, P).astype(np.int64)
+    build = np.random.permutation(B).astype(np.int64)
+    bins = world * nlocal
+    stride = 2 * (bins + 1)
+    shards, allc = [], torch.zeros(world * stride, dtype=torch.int64, device="cuda")
+    for r in range(world):
+        plo, phi = D.shard_bounds(P, world, r)
+        blo, bhi = D.shard_bounds(B, world, r)
+        pk, bk = torch.from_numpy(probe[plo:phi]).cuda(), torch.from_numpy(build[blo:bhi]).cuda()
+        mine = allc[r * stride:(r + 1) * stride]
+        ops.xjoin_count_dev(bk, world, nlocal, mine[:bins + 1])
+        ops.xjoin_count_dev(pk, world, nlocal, mine[bins + 1:])
+        cb, hi_b = ops.xjoin_count(bk, world, nlocal)
+        cp, _ = ops.xjoin_count(pk, world, nlocal)
+        assert mine.cpu().tolist() == cb + [hi_b] + cp + [0]
+        shards.append((pk, plo, bk, blo))
+    M = allc.view(world, stride).cpu().numpy()
+    counts_b, counts_p = M[:, :bins].tolist(), M[:, bins + 1:2 * bins + 1].tolist()
+    recv_b = D.plan_fused_exchange(counts_b, world, nlocal, 0)[2]
+    recv_p = D.plan_fused_exchange(counts_p, world, nlocal, 0)[2]
+    cap_b, cap_p = max(recv_b), max(recv_p)
+    buf_b = [torch.full((cap_b, 2), -7, dtype=torch.int32, device="cuda") for _ in range(world)]
+    buf_p = [torch.full((cap_p, 2), -7, dtype=torch.int32, device="cuda") for _ in range(world)]
+    off = torch.zeros(2 * bins, dtype=torch.int64, device="cuda")
+    status = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for r, (pk, plo, bk, blo) in enumerate(shards):
+        # too small a buffer: flagged, and the scatter leaves the buffers untouched
+        ops.xjoin_plan_dev(allc, world, nlocal, r, cap_b, cap_p - 1, off[:bins], off[bins:], status)
+        assert status.cpu().tolist() == [0, 1]
+        if r == 0:                                   # nothing has been written yet
+            ops.xjoin_scatter_dev(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], off[bins:], status)
+            assert all(bool((t == -7).all()) for t in buf_p)
+        ops.xjoin_plan_dev(allc, world, nlocal, r, cap_b, cap_p, off[:bins], off[bins:], status)
+        assert status.cpu().tolist() == [0, 0]
+        want_b, want_p = D.plan_fused_exchange(counts_b, world, nlocal, r)[0], D.plan_fused_exchange(counts_p, world, nlocal, r)[0]
+        assert off.cpu().tolist() == want_b + want_p
+        ops.xjoin_scatter_dev(bk, blo, world, nlocal, [t.data_ptr() for t in buf_b], off[:bins], status)
+        ops.xjoin_scatter_dev(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], off[bins:], status)
+    torch.cuda.synchronize()
+    got_l, got_r = [], []
+    for d in range(world):
+        tot_b = D.plan_fused_exchange(counts_b, world, nlocal, d)[1]
+        tot_p = D.plan_fused_exchange(counts_p, world, nlocal, d)[1]
+        assert bool((buf_b[d][:recv_b[d], 1] >= 0).all()) and bool((buf_p[d][:recv_p[d], 1] >= 0).all())
+        if d % 2:      # the two-stage form: tables filled on the library's private stream, then the probe waits for them
+            handle = ops.xjoin_build(buf_b[d].data_ptr(), tot_b, nlocal, True)
+            gl, gr = ops.xjoin_probe(handle, buf_p[d].data_ptr(), tot_p)
+        else:
+            gl, gr = ops.xjoin_local(buf_p[d].data_ptr(), tot_p, buf_b[d].data_ptr(), tot_b, nlocal)
+        got_l.append(gl.cpu().numpy()), got_r.append(gr.cpu().numpy())
+    gl, gr = np.concatenate(got_l), np.concatenate(got_r)
+    ol, orr = oracle.join(oracle.JOIN_INNER, [probe], [build])
+    got, want = np.stack([gl, gr], 1), np.stack([ol, orr], 1)
+    np.testing.assert_array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
+    # a wide build key anywhere: flagged
+    allc[bins] = 5
+    ops.xjoin_plan_dev(allc, world, nlocal, 0, cap_b, cap_p, off[:bins], off[bins:], status)
+    assert status.cpu().tolist()[0] == 1

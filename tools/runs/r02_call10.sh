@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+set -u
+OUT=gpurun_out; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_dist_gpu.py tests/test_join_gpu.py tests/test_reference_parity.py -m gpu -x -q > $OUT/t_join.log 2>&1; echo "pytest rc=$?"; tail -5 $OUT/t_join.log
+timeout 300 python bench.py --only join --no-e2e --no-cpu > $OUT/join_ship.json 2> $OUT/join_ship.err; echo "ship rc=$?"; python tools/show_bench.py $OUT/join_ship.json
+tools/bin/microbench > $OUT/microbench.txt 2>&1; echo "microbench rc=$?"

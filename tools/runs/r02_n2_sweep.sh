@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+set -u
+N=${1:-2}
+OUT=gpurun_out; mkdir -p $OUT
+run() { tag=$1; shift
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+     bench.py --gpus $N --steps 5 --warmup 3 --only join --no-e2e "$@" > $OUT/sweep_n${N}_$tag.json 2> $OUT/sweep_n${N}_$tag.err
+  echo "$tag rc=$?"; python tools/show_bench.py $OUT/sweep_n${N}_$tag.json | head -3; }
+run rpp20
+run rpp21 --xjoin-rpp-log2 21
+run rpp22 --xjoin-rpp-log2 22
+run twopass --two-pass
