@@ -59,6 +59,7 @@ def parse_args():
                     "the one-pass exchange (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: fill the hash tables after the exchange instead of beside it")
     ap.add_argument("--scatter-ctas", type=int, default=-1, help="N > 1: CTAs per SM of the probe-side scatter while the tables are built (0 = all)")
+    ap.add_argument("--symm-mem", action="store_true", help="N > 1: receive buffers from torch symmetric memory (VMM) instead of CUDA IPC")
     ap.add_argument("--two-pass", action="store_true", help="N > 1: round 1's exchange (partition by destination, then again locally)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -721,6 +722,7 @@ def bench_dist(args, rank, world, local_rank):
             peer = D.PeerExchange(ops)
             peer.one_pass = not args.two_pass
             peer.overlap_build = not args.no_overlap
+            peer.use_symm_mem = args.symm_mem
             if args.scatter_ctas >= 0:
                 peer.scatter_ctas_per_sm = args.scatter_ctas
             if args.xjoin_rpp_log2:

@@ -451,6 +451,119 @@ part_scatter32_kernel(const KT* __restrict__ keys, const gdf_valid_type* __restr
   }
 }
 
+// ---- compact scatter for the fused exchange: per-bin runs leave the SM as TMA bulk stores ----
+// tools/p2p_bench.cu (profiles/r02_p2p_store_bench.txt): the element-parallel copy-out above - a warp instruction stores
+// 32 consecutive staged pairs, which straddle bin boundaries and start at arbitrary 8-byte offsets - reaches 446 GB/s
+// of peer stores over NVLink (the SM's outstanding store requests carry ~70 useful bytes each), exactly what the
+// exchange measured; cp.async.bulk shared -> global reaches 716 GB/s (the copy-engine rate) for runs as short as
+// 128 bytes, because the TMA engine emits whole lines.  So here ONE thread per bin issues ONE bulk store per tile.
+// Bulk copies need 16-byte aligned addresses on both sides and a multiple of 16 bytes; pairs are 8 bytes, so:
+//   * the bin's reserved global position (gbase, from the cursor atomic) must be known BEFORE the tile is staged: its
+//     parity decides where the run sits in shared memory (slot start even, run at slot start + parity), so that the
+//     even-aligned body of the run is 16-byte aligned in shared AND global memory; an odd head / tail pair is one
+//     plain 8-byte store.  The atomic's latency is exposed once per tile - immaterial here, the kernel is NVLink-bound;
+//   * a slot is the run rounded up to an even length (+ parity), so the staged tile needs up to 2 extra pairs per bin.
+struct Scatter32BulkSmem {
+  uint2 pairs[kS32Tile + 2 * kMaxParts];
+  unsigned hist[2][kMaxParts];
+  unsigned lstart[kMaxParts];
+  unsigned long long gbase[kMaxParts];
+};
+
+template <typename KT>
+__global__ void __launch_bounds__(kS32Threads, 3)
+part_scatter32_bulk_kernel(const KT* __restrict__ keys, size_t n, PartGeom g, unsigned long long* __restrict__ cursors,
+                           int32_t id_base, const PeerPairs peer) {
+  extern __shared__ __align__(128) unsigned char scatter32b_smem[];
+  Scatter32BulkSmem& sm = *reinterpret_cast<Scatter32BulkSmem*>(scatter32b_smem);
+  if (peer.status != nullptr && (peer.status[0] | peer.status[1]) != 0) return;  // the device-side plan said "do not write"
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const size_t tiles = (n + kS32Tile - 1) / kS32Tile;
+  for (unsigned p = threadIdx.x; p < 2 * kMaxParts; p += kS32Threads) (&sm.hist[0][0])[p] = 0;
+  __syncthreads();
+  unsigned buf = 0;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1u) {
+    const size_t wbase = tile * kS32Tile + (size_t)warp * (32 * kS32Rows);
+    uint32_t k[kS32Rows];
+    unsigned wide = 0;
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      const size_t r = wbase + (size_t)i * 32 + lane;
+      const KT kk = r < n ? keys[r] : (KT)0;
+      k[i] = (uint32_t)kk;
+      if (sizeof(KT) == 8 && (uint32_t)((unsigned long long)kk >> 32) != 0) wide |= 1u << i;
+    }
+    unsigned rp[kS32Rows];  // rank << 16 | bin, 0xffff = dropped (past the end / key wider than 32 bits: it cannot match)
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      const size_t r = wbase + (size_t)i * 32 + lane;
+      const bool keep = r < n && !((wide >> i) & 1u);
+      const unsigned p = keep ? g.pid(KeyBits<uint32_t>::hash(k[i])) : 0u;
+      rp[i] = keep ? ((atomicAdd(&sm.hist[buf][p], 1u) << 16) | p) : 0xffffu;
+    }
+    __syncthreads();  // (1) tile histogram complete
+    {
+      const unsigned p = threadIdx.x;
+      if (p < g.nparts) {
+        const unsigned run = sm.hist[buf][p];
+        sm.gbase[p] = run ? atomicAdd(&cursors[p], (unsigned long long)run) : 0ull;
+        tma::bulk_wait_read_all();  // this thread's bulk store of the previous tile has finished reading shared memory
+      }
+      if (p < kMaxParts) sm.hist[buf ^ 1u][p] = 0;  // the other buffer, for the next tile
+    }
+    __syncthreads();  // (2a) reserved positions known, the previous tile's staged pairs are free
+    if (warp == kS32Threads / 32 - 1) {  // slot starts: exclusive scan of the even slot lengths (8 bins per lane)
+      unsigned c[kMaxParts / 32], tot = 0;
+#pragma unroll
+      for (int j = 0; j < (int)(kMaxParts / 32); ++j) {
+        const unsigned p = lane * (kMaxParts / 32) + j;
+        c[j] = p < g.nparts ? ((sm.hist[buf][p] + ((unsigned)sm.gbase[p] & 1u) + 1u) & ~1u) : 0;
+        tot += c[j];
+      }
+      unsigned inc = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += o;
+      }
+      unsigned run = inc - tot;
+#pragma unroll
+      for (int j = 0; j < (int)(kMaxParts / 32); ++j) {
+        const unsigned p = lane * (kMaxParts / 32) + j;
+        if (p < g.nparts) sm.lstart[p] = run + ((unsigned)sm.gbase[p] & 1u);  // the run starts at the slot + parity
+        run += c[j];
+      }
+    }
+    __syncthreads();  // (2b) run starts visible
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      if ((rp[i] & 0xffffu) == 0xffffu) continue;
+      const unsigned p = rp[i] & 0xffffu;
+      const size_t row = wbase + (size_t)i * 32 + lane;
+      sm.pairs[sm.lstart[p] + (rp[i] >> 16)] = make_uint2(k[i], (uint32_t)((int32_t)row + id_base));
+    }
+    tma::fence_proxy_async();  // the staged pairs are read by the copy engine
+    __syncthreads();           // (3) staged tile complete
+    {
+      const unsigned p = threadIdx.x;
+      unsigned len = p < g.nparts ? sm.hist[buf][p] : 0u;
+      if (len) {
+        uint2* dst = peer.base[p >> peer.shift] + sm.gbase[p];
+        const uint2* src = &sm.pairs[sm.lstart[p]];
+        if ((unsigned)sm.gbase[p] & 1u) {  // odd head pair: plain store; what follows is 16-byte aligned on both sides
+          *dst = *src;
+          ++dst, ++src, --len;
+        }
+        const unsigned body = len & ~1u;
+        if (body) tma::bulk_store(dst, src, body * (unsigned)sizeof(uint2));
+        if (len & 1u) dst[body] = src[body];
+        tma::bulk_commit();
+      }
+    }
+  }
+  tma::bulk_wait_all();
+}
+
 #include "join_compact.cuh"
 
 // Where the pairs of one side live.  rows == nullptr means "not partitioned": key i belongs to row i
@@ -1146,7 +1259,25 @@ gdf_error partition_scatter32(const gdf_column* col, PartGeom g, const unsigned 
   if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
   const size_t cap = (size_t)sm_count() * (size_t)(per_sm > 0 ? per_sm : 1);
   const int sblocks = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
-  {
+  // single-GPU path: the same bulk-store kernel with one destination (measured at C3: 4.83 -> 4.38 ms for both sides;
+  // the element-parallel copy-out kept the LSU at 74 %, profiles/r02a_ncu_join_full.md)
+  if (!peer.on && out_pairs != nullptr && lab_knob("B200_SCATTER_BULK", 1) != 0) {
+    peer.on = 1;
+    peer.shift = 8;  // bin >> 8 == 0: everything goes to base[0]
+    peer.base[0] = out_pairs;
+  }
+  if (peer.on && !KEEP_NULLS && col->valid == nullptr && payload == nullptr) {  // the fused exchange: TMA bulk stores per bin
+    auto bkern = part_scatter32_bulk_kernel<KT>;
+    const size_t bsmem = sizeof(Scatter32BulkSmem);
+    B200_CUDA_TRY(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    int bper_sm = 1;
+    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bper_sm, bkern, kS32Threads, bsmem));
+    if (ctas_per_sm > 0 && ctas_per_sm < bper_sm) bper_sm = ctas_per_sm;
+    const size_t bcap = (size_t)sm_count() * (size_t)(bper_sm > 0 ? bper_sm : 1);
+    const int bblocks = (int)(tiles < bcap ? (tiles ? tiles : 1) : bcap);
+    B200_TIMED("join_part_scatter");
+    bkern<<<bblocks, kS32Threads, bsmem>>>(keys, n, g, d_cursors, id_base, peer);
+  } else {
     B200_TIMED("join_part_scatter");
     kern<<<sblocks, kS32Threads, smem_bytes>>>(keys, col->valid, n, g, d_cursors, out_pairs, payload, id_base, peer);
   }

@@ -70,5 +70,8 @@ static __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// (the destination of bulk_store may be peer memory: the TMA engine writes whole lines over NVLink, tools/p2p_bench.cu)
+static __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+static __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 }  // namespace tma
 }  // namespace b200

@@ -279,6 +279,7 @@ class PeerExchange(object):
         self.one_pass = True                  # fused_inner_join (one partition pass per side) before the two-pass path
         self.async_plan = True                # steady state keeps counts / plan on the device (no host round trips)
         self._async_state = {}
+        self.use_symm_mem = False             # receive buffers from torch symmetric memory instead of cudaMalloc + CUDA IPC
         self.overlap_build = True             # fill the hash tables on a second stream during the probe side's exchange
         self.scatter_ctas_per_sm = 2          # ... whose scatter then leaves a third of every SM to the table build
         self.rows_per_partition = 1 << 20     # build rows per receiver-local partition of the one-pass exchange
@@ -340,6 +341,9 @@ class PeerExchange(object):
     def _release(self, slot):
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
+        if slot.get("symm"):
+            slot.pop("symm")
+            return
         for r in range(self.world):
             if r != self.rank:
                 for peers in slot["peers"]:
@@ -361,6 +365,14 @@ class PeerExchange(object):
         if slot:
             self._release(slot)
         cap = max(1 << 20, (rows + (rows >> 3) + (1 << 20) - 1) >> 20 << 20)
+        if self.use_symm_mem:    # torch symmetric memory (CUDA VMM allocations exchanged as file descriptors) instead of legacy IPC
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(cap * 2, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+            hdl = symm.rendezvous(t, group=self.group if self.group is not None else dist.group.WORLD)
+            peers = [int(p) for p in hdl.buffer_ptrs]
+            slot = {"cap": cap, "itemsize": 8, "pairs": True, "mine": (int(t.data_ptr()),), "peers": (peers,), "symm": (t, hdl)}
+            self.slots[name] = slot
+            return slot
         ptr, h = self.ops.peer_alloc(cap * 8)
         handles = [None] * self.world
         dist.all_gather_object(handles, h, group=self.group)
