@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every row count (debug only)")
-    ap.add_argument("--only", default="", help="comma list of join,groupby,filter (debug only)")
+    ap.add_argument("--only", default="", help="comma list of workload keys (join, groupby, groupby_uniform, groupby_all, filter, "
+                    "filter_stencil, reduce_sum, add_c1, hash_partition, join_result_cols, c5, ...; debug only)")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N>1: rows cross NVLink inside the partition kernel (peer memory) or via NCCL all_to_all")
     ap.add_argument("--lab", action="store_true", help="load the -DB200_LAB build (libgdf_b200/lib_lab, make LAB=1): "
@@ -520,6 +521,115 @@ class ReduceWorkload(object):
         return got == want
 
 
+class BinaryAddWorkload(object):
+    """a16: gdf_add_i64 on two int64 columns (C1 is the same call at 1M int32 rows: 12 MB, launch-latency bound)."""
+
+    def __init__(self, api, scale, rows, dtype=torch.int64):
+        self.api, self.N, self.dtype = api, max(int(rows * scale), 1024), dtype
+        w = 8 if dtype == torch.int64 else 4
+        self.name = "a16 gdf_add_%s over %.1e rows" % ("i64" if w == 8 else "i32", self.N)
+        self.a = torch.randint(-10000, 10000, (self.N,), generator=gen(11), device="cuda", dtype=dtype)
+        self.b = torch.randint(-10000, 10000, (self.N,), generator=gen(12), device="cuda", dtype=dtype)
+        self.o = torch.empty_like(self.a)
+        self.rows_per_step, self.w = self.N, w
+
+    def step(self):
+        lib = self.api.lib
+        fn = lib.gdf_add_i64 if self.w == 8 else lib.gdf_add_i32
+        self.api.check(fn(self.api.column(self.a), self.api.column(self.b), self.api.column(self.o)), "gdf_add")
+
+    def algorithmic_bytes(self):
+        return 3 * self.w * self.N
+
+    def check(self):
+        self.step()
+        return bool((self.o == self.a + self.b).all())
+
+
+class HashPartitionWorkload(object):
+    """a17: gdf_hash_partition of (int64 key, int64 payload) rows into 8 partitions (MurmurHash3 row hash)."""
+
+    def __init__(self, api, scale, rows=2.5e8, nparts=8):
+        self.api, self.N, self.nparts = api, max(int(rows * scale), 1024), nparts
+        self.name = "a17 gdf_hash_partition %.1e rows x (int64 key, int64 payload) -> %d partitions" % (self.N, nparts)
+        self.k = torch.randint(0, 1 << 40, (self.N,), generator=gen(13), device="cuda", dtype=torch.int64)
+        self.v = torch.arange(self.N, device="cuda", dtype=torch.int64)
+        self.ok, self.ov = torch.empty_like(self.k), torch.empty_like(self.v)
+        self.rows_per_step = self.N
+        self.offsets = None
+
+    def step(self):
+        ffi, lib = self.api.ffi, self.api.lib
+        self._ins = [self.api.column(self.k), self.api.column(self.v)]     # cffi arrays of pointers do not keep their targets alive
+        ins = ffi.new("gdf_column*[]", self._ins)
+        self._outs = [self.api.column(self.ok), self.api.column(self.ov)]
+        outs = ffi.new("gdf_column*[]", self._outs)
+        offs = ffi.new("int[]", self.nparts)
+        self.api.check(lib.gdf_hash_partition(2, ins, ffi.new("int[]", [0]), 1, self.nparts, outs, offs, lib.GDF_HASH_MURMUR3),
+                       "gdf_hash_partition")
+        self.offsets = list(offs)
+
+    def algorithmic_bytes(self):
+        return 2 * 16 * self.N
+
+    def check(self):
+        """rows keep their (key, payload) pairing; partition sizes add up; the payload is a permutation."""
+        self.step()
+        ok = self.offsets[0] == 0 and all(a <= b for a, b in zip(self.offsets, self.offsets[1:] + [self.N]))
+        ok = ok and bool((self.k[self.ov] == self.ok).all())
+        return ok and int(self.ov.sum().item()) == self.N * (self.N - 1) // 2
+
+
+class JoinGatherWorkload(object):
+    """f1: gdf_inner_join with result_cols - [left payload, key, right payload] materialised by the fused gather."""
+
+    def __init__(self, api, scale, P=2e8, B=2e7):
+        self.api, self.P, self.B = api, max(int(P * scale), 4096), max(int(B * scale), 1024)
+        self.name = "f1 gdf_inner_join %.0e x %.0e int64 + result_cols (int64 payload on both sides)" % (self.P, self.B)
+        self.build = torch.randperm(self.B, generator=gen(14), device="cuda", dtype=torch.int64)
+        self.probe = torch.randint(0, self.B, (self.P,), generator=gen(15), device="cuda", dtype=torch.int64)
+        self.lp = torch.arange(self.P, device="cuda", dtype=torch.int64) * 3
+        self.rp = torch.arange(self.B, device="cuda", dtype=torch.int64) * 7
+        ffi, lib = api.ffi, api.lib
+        self.ctx = ffi.new("gdf_context*")
+        lib.gdf_context_view(self.ctx, 0, lib.GDF_HASH, 0, 0, 0)
+        self.rows_per_step = self.P + self.B
+        self.pairs = None
+
+    def call(self):
+        ffi, lib = self.api.ffi, self.api.lib
+        self._cols = [self.api.column(t) for t in (self.lp, self.probe, self.build, self.rp)]
+        la, ra = ffi.new("gdf_column*[]", self._cols[:2]), ffi.new("gdf_column*[]", self._cols[2:])
+        self.res = [ffi.new("gdf_column*") for _ in range(3)]
+        self.out_l, self.out_r = ffi.new("gdf_column*"), ffi.new("gdf_column*")
+        self.api.check(lib.gdf_inner_join(la, 2, ffi.new("int[]", [1]), ra, 2, ffi.new("int[]", [0]), 1, 3,
+                                          ffi.new("gdf_column*[]", self.res), self.out_l, self.out_r, self.ctx), "gdf_inner_join")
+        self.pairs = int(self.out_l.size)
+
+    def free(self):
+        for c in self.res + [self.out_l, self.out_r]:
+            if c.data != self.api.ffi.NULL:
+                self.api.lib.gdf_column_free(c)
+
+    def step(self):
+        self.call()
+        self.free()
+
+    def algorithmic_bytes(self):   # the join's own 8 B/row in + 8 B/pair out, plus 3 materialised int64 columns
+        return 8 * (self.P + self.B) + 8 * self.pairs + 3 * 8 * self.pairs
+
+    def check(self):
+        self.call()
+        n, ffi = self.pairs, self.api.ffi
+        li, ri = alias(ffi, self.out_l.data, n, np.int32).long(), alias(ffi, self.out_r.data, n, np.int32).long()
+        a, k, b = (alias(ffi, c.data, n, np.int64) for c in self.res)
+        ok = n == self.P and bool((a == self.lp[li]).all()) and bool((k == self.probe[li]).all()) and bool((b == self.rp[ri]).all())
+        ok = ok and bool((self.probe[li] == self.build[ri]).all())
+        del li, ri, a, k, b
+        self.free()
+        return ok
+
+
 class C5Workload(object):
     name = "C5 gdf_left_join composite (int64,int32) key, 30 % null rows, 5e8 x 5e7"
 
@@ -622,18 +732,27 @@ def run_workload(api, wl, args, peak_gbs, clocks):
 
 # per-kernel algorithmic bytes per launch (compulsory reads + writes of THAT kernel), see DESIGN.md
 def kernel_bytes(name, wl):
-    if isinstance(wl, JoinWorkload):
+    """Algorithmic bytes of ONE launch of the kernel(s) timed under `name`: what that kernel must read and write."""
+    if isinstance(wl, JoinWorkload):   # C3 takes the compact path: 8-byte {key32, tag32} pairs, 8-byte slots
         P, B, pairs = wl.P, wl.B, wl.pairs
-        table = {"join_part_hist": None, "join_part_scatter": None}
         if name == "join_part_probe":
-            return 12 * P + 8 * pairs            # {key,row} pairs in, index pairs out
+            return 8 * P + 8 * pairs             # pairs in, index pairs out
         if name == "join_part_scatter":
-            return (8 + 12) * (P + B) / 2.0      # two launches per step (build side, probe side): average
+            return (8 + 8) * (P + B) / 2.0       # two launches per step (build side, probe side): average
         if name == "join_part_hist":
             return 8 * (P + B) / 2.0
         if name == "join_part_build":
-            return 12 * B + 16 * B
-        return table.get(name)
+            return 8 * B + 8 * 2 * B             # pairs in, slots (load factor 0.5) written
+        return None
+    if isinstance(wl, BinaryAddWorkload) and name == "binary_op":
+        return wl.algorithmic_bytes()
+    if isinstance(wl, HashPartitionWorkload) and name == "hash_partition":
+        return wl.algorithmic_bytes()
+    if isinstance(wl, JoinGatherWorkload):
+        if name == "join_gather":
+            return (4 + 8 + 8) * wl.pairs * 3 / 2.0   # two launches (left side: payload + key, right side: payload): index in, value in, value out
+        if name == "join_part_probe":
+            return 8 * wl.P + 8 * wl.pairs
     if isinstance(wl, GroupbyWorkload):
         if name == "groupby_build_fast":
             return 16 * wl.N
@@ -659,16 +778,34 @@ def kernel_bytes(name, wl):
     return None
 
 
-def measured_traffic(kernel, scale):
-    """DRAM bytes per launch from the committed full-size ncu capture (profiles/r01c_traffic_full_size.json)."""
-    path = os.path.join(ROOT, "profiles", "r01c_traffic_full_size.json")
-    if scale != 1.0 or not os.path.isfile(path):
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic_full_size.json")
+
+
+def csrc_sha1():
+    """Hash of the kernel sources: a traffic record only describes the kernels it was captured from."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for path in sorted(glob.glob(os.path.join(ROOT, "libgdf_b200", "csrc", "*"))):
+        if path.endswith((".cu", ".cuh", ".h", ".cpp")):
+            h.update(os.path.basename(path).encode())
+            h.update(open(path, "rb").read())
+    return h.hexdigest()
+
+
+def measured_traffic(workload_key, kernel, scale):
+    """DRAM bytes per launch from the full-size ncu capture (tools/traffic_full.sh -> profiles/r02_traffic_full_size.json).
+    The file records the hash of csrc/ it was captured from; a record from other sources is stale and is NOT reported."""
+    if scale != 1.0 or not os.path.isfile(TRAFFIC_FILE):
         return None
-    rec = json.load(open(path)).get(kernel)
+    data = json.load(open(TRAFFIC_FILE))
+    if data.get("csrc_sha1") != csrc_sha1():
+        return None
+    rec = data.get("entries", {}).get(workload_key, {}).get(kernel)
     return (rec["dram_read"] + rec["dram_write"]) if rec else None
 
 
-def roofline_for(res, wl, peak_gbs, peak_kind, scale=1.0):
+def roofline_for(res, wl, peak_gbs, peak_kind, scale=1.0, key=None):
     ks = res["kernels"]
     if not ks:
         return None
@@ -679,7 +816,7 @@ def roofline_for(res, wl, peak_gbs, peak_kind, scale=1.0):
         return {"kernel": top, "bound": "hbm", "achieved": None, "peak": peak_gbs, "unit": "GB/s", "frac": None, "traffic": None}
     achieved = nbytes / 1e9 / (per_launch_ms * 1e-3)
     return {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": measured_traffic(top, scale), "peak_source": peak_kind,
+            "frac": achieved / peak_gbs, "traffic": measured_traffic(key, top, scale), "peak_source": peak_kind,
             "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": per_launch_ms,
             "share_of_step": ks[top]["ms_per_step"] / res["ms_per_step"]}
 
@@ -1060,7 +1197,7 @@ def main():
                     "config": {"workload": wl.name, "probe_rows": wl.P, "build_rows": wl.B, "key_dtype": "int64",
                                "rows_counted": "probe+build", "l2_policy": "inputs (8.8 GB) larger than L2, no flush",
                                "rmm": "pool"}})
-        roof = roofline_for(res, wl, peak_gbs, peak_kind, args.scale)
+        roof = roofline_for(res, wl, peak_gbs, peak_kind, args.scale, "join")
         if roof:
             out["roofline"] = roof
         out["gpu_launches"] = int(round(sum(k["launches_per_step"] for k in res["kernels"].values()) * args.steps)) if res["kernels"] else None
@@ -1090,7 +1227,7 @@ def main():
         torch.cuda.empty_cache()
 
     # ---- C4 group-by sum ----
-    if not only or "groupby" in only:
+    if not only or any(k.startswith("groupby") for k in only):
         import copy
         # (name, kwargs, args override): the b200 arm runs C4 itself (Zipf) and the uniform-key variant at 1e9 rows;
         # the reference arm is bounded: its table is 2N x 16 B and its int grid-stride arithmetic is unsafe above 2^29
@@ -1105,6 +1242,8 @@ def main():
             plan = [("groupby", dict(), args), ("groupby_uniform", dict(zipf=False), args),
                     ("groupby_uniform_5e8", dict(rows=5e8, zipf=False), args)]
         for key, kw, a in plan:
+            if only and key not in only and "groupby_all" not in only:
+                continue
             try:
                 wl = GroupbyWorkload(api, args.scale, **kw)
                 ok = wl.check()
@@ -1112,7 +1251,7 @@ def main():
                 res["parity_properties_ok"] = ok
                 res["groups"] = wl.groups
                 res["steps"], res["warmup"] = a.steps, a.warmup
-                res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale)
+                res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale, key)
                 workloads[key] = res
                 del wl
             except Exception as exc:
@@ -1127,7 +1266,7 @@ def main():
             res = run_workload(api, wl, args, peak_gbs, clocks)
             res["parity_properties_ok"] = ok
             res["selected"] = wl.selected
-            res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale)
+            res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale, "filter")
             workloads["filter"] = res
             del wl
         except Exception as exc:
@@ -1138,6 +1277,10 @@ def main():
         extra = [("filter_stencil", lambda: StencilWorkload(api, args.scale), lambda wl: {"selected": wl.selected}),
                  ("reduce_sum", lambda: ReduceWorkload(api, args.scale, False), lambda wl: {}),
                  ("reduce_sum_masked", lambda: ReduceWorkload(api, args.scale, True), lambda wl: {}),
+                 ("add_c1", lambda: BinaryAddWorkload(api, 1.0, 1e6, torch.int32), lambda wl: {}),
+                 ("add_i64_2.5e8", lambda: BinaryAddWorkload(api, args.scale, 2.5e8), lambda wl: {}),
+                 ("hash_partition", lambda: HashPartitionWorkload(api, args.scale), lambda wl: {}),
+                 ("join_result_cols", lambda: JoinGatherWorkload(api, args.scale), lambda wl: {"output_pairs": wl.pairs}),
                  ("c5", lambda: C5Workload(api, args.scale), lambda wl: {"output_pairs": wl.pairs})]
         for key, make, more in extra:
             if only and key not in only:
@@ -1148,7 +1291,7 @@ def main():
                 res = run_workload(api, wl, args, peak_gbs, clocks)
                 res["parity_properties_ok"] = ok
                 res.update(more(wl))
-                res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale)
+                res["roofline"] = roofline_for(res, wl, peak_gbs, peak_kind, args.scale, key)
                 workloads[key] = res
                 del wl
             except Exception as exc:

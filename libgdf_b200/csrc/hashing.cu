@@ -112,15 +112,26 @@ static __device__ __forceinline__ void move_value(const ColumnMove& m, int c, si
   }
 }
 
+// Pass 2.  SMEM (P <= 2048): the tile's rows are first ORDERED by partition in shared memory (order[j] = row of the tile
+// that lands at sorted position j, ppos[j] = its partition), then every column is moved with consecutive threads on
+// consecutive sorted positions - which are consecutive output addresses inside a partition's run - so the stores of a
+// warp are coalesced runs instead of 32 scattered elements, and the loads stay inside the tile's own 2048-row window of
+// the input column (every fetched sector is used).  The first version moved rows in input order with one scattered
+// store per row and column: 1.7 TB/s at 2.5e8 x (int64, int64) rows into 8 partitions (profiles/r02_notes.md).
 template <bool IDENTITY, bool SMEM>
 __global__ void __launch_bounds__(kThreads) partition_scatter_kernel(TableView keys, Partitioner part,
                                                                      ColumnMove mv,
                                                                      unsigned* __restrict__ cursors) {
   extern __shared__ unsigned sm[];
-  unsigned* hist = sm;            // rows of this tile per partition, then reused as rank source
-  unsigned* base = sm + part.n;   // reserved global start of this tile's run per partition
+  unsigned* hist = sm;                 // rows of this tile per partition
+  unsigned* base = sm + part.n;        // reserved global start of this tile's run per partition
+  unsigned* lstart = sm + 2 * part.n;  // start of the partition's run inside the sorted tile
+  unsigned short* order = reinterpret_cast<unsigned short*>(sm + 3 * part.n);  // [kTileRows]
+  unsigned short* ppos = order + kTileRows;                                    // [kTileRows]
+  __shared__ unsigned warp_sums[kThreads / 32];
   const size_t rows = keys.rows;
   const size_t tiles = (rows + kTileRows - 1) / kTileRows;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const size_t tile_base = tile * kTileRows;
     unsigned pid[kRowsPerThread], rank[kRowsPerThread];
@@ -136,21 +147,64 @@ __global__ void __launch_bounds__(kThreads) partition_scatter_kernel(TableView k
         rank[i] = SMEM ? atomicAdd(&hist[pid[i]], 1u) : atomicAdd(&cursors[pid[i]], 1u);
       }
     }
-    if (SMEM) {
-      __syncthreads();
-      for (unsigned p = threadIdx.x; p < part.n; p += kThreads)
-        if (hist[p]) base[p] = atomicAdd(&cursors[p], hist[p]);
-      __syncthreads();
-    }
+    if (!SMEM) {  // too many partitions for shared memory: rows move in input order, positions from global cursors
 #pragma unroll 1
-    for (int c = 0; c < mv.ncols; ++c) {
+      for (int c = 0; c < mv.ncols; ++c) {
 #pragma unroll
-      for (int i = 0; i < kRowsPerThread; ++i) {
-        const size_t r = tile_base + (size_t)i * kThreads + threadIdx.x;
-        if (r < rows) move_value(mv, c, r, (SMEM ? base[pid[i]] : 0u) + rank[i]);
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          const size_t r = tile_base + (size_t)i * kThreads + threadIdx.x;
+          if (r < rows) move_value(mv, c, r, rank[i]);
+        }
+      }
+      continue;
+    }
+    __syncthreads();
+    {  // reserve the runs (one global atomic per non-empty partition) and scan the tile's counts
+      const unsigned per = (part.n + kThreads - 1) / kThreads;
+      const unsigned lo = threadIdx.x * per, hi = min(part.n, lo + per);
+      unsigned sum = 0;
+      for (unsigned p = lo; p < hi; ++p) {
+        const unsigned h = hist[p];
+        if (h) base[p] = atomicAdd(&cursors[p], h);
+        sum += h;
+      }
+      unsigned inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += o;
+      }
+      if (lane == 31) warp_sums[warp] = inc;
+      __syncthreads();
+      unsigned off = 0;
+      for (unsigned w = 0; w < warp; ++w) off += warp_sums[w];
+      unsigned run = off + inc - sum;
+      for (unsigned p = lo; p < hi; ++p) {
+        lstart[p] = run;
+        run += hist[p];
       }
     }
-    if (SMEM) __syncthreads();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const size_t r = tile_base + (size_t)i * kThreads + threadIdx.x;
+      if (r < rows) {
+        const unsigned j = lstart[pid[i]] + rank[i];
+        order[j] = (unsigned short)(i * kThreads + threadIdx.x);
+        ppos[j] = (unsigned short)pid[i];
+      }
+    }
+    __syncthreads();
+    const unsigned live = (unsigned)(rows - tile_base < (size_t)kTileRows ? rows - tile_base : (size_t)kTileRows);
+#pragma unroll 1
+    for (int c = 0; c < mv.ncols; ++c) {
+#pragma unroll 4
+      for (unsigned j = threadIdx.x; j < live; j += kThreads) {
+        const unsigned p = ppos[j];
+        move_value(mv, c, tile_base + order[j], (size_t)base[p] + (j - lstart[p]));
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -178,7 +232,7 @@ gdf_error run_partition(const TableView& keys, const ColumnMove& mv, int num_par
   partition_scan_kernel<<<1, 1024>>>(totals, part.n, d_offsets, cursors);
   B200_CHECK_LAST();
   if (smem)
-    partition_scatter_kernel<IDENTITY, true><<<blocks, kThreads, 2 * P * sizeof(unsigned)>>>(keys, part, mv, cursors);
+    partition_scatter_kernel<IDENTITY, true><<<blocks, kThreads, 3 * P * sizeof(unsigned) + 2 * kTileRows * sizeof(unsigned short)>>>(keys, part, mv, cursors);
   else
     partition_scatter_kernel<IDENTITY, false><<<blocks, kThreads>>>(keys, part, mv, cursors);
   B200_CHECK_LAST();

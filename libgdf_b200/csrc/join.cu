@@ -441,35 +441,68 @@ struct GatherCols {
   int ncols;
 };
 
-// One thread per 8 output rows so that each thread owns one whole output validity byte (no atomics).
+// One thread per output row, four rows in flight per thread: index reads and value stores of a warp are coalesced, the
+// four random value loads of a thread are all issued before the first store, and the validity bits of a warp's 32 rows
+// come from one ballot - lanes 0..3 each own one whole output byte, so no atomics.  (Round 1: one thread per 8 rows,
+// every store waiting for its own load, stores of a warp 64 bytes apart: 3.8 ms per 2e8-row int64 column.)
+static __device__ __forceinline__ uint64_t gather_load(const void* col, int width, size_t i) {
+  switch (width) {
+    case 1: return static_cast<const uint8_t*>(col)[i];
+    case 2: return static_cast<const uint16_t*>(col)[i];
+    case 4: return static_cast<const uint32_t*>(col)[i];
+    default: return static_cast<const uint64_t*>(col)[i];
+  }
+}
+static __device__ __forceinline__ void gather_store(void* col, int width, size_t i, uint64_t v) {
+  switch (width) {
+    case 1: static_cast<uint8_t*>(col)[i] = (uint8_t)v; break;
+    case 2: static_cast<uint16_t*>(col)[i] = (uint16_t)v; break;
+    case 4: static_cast<uint32_t*>(col)[i] = (uint32_t)v; break;
+    default: static_cast<uint64_t*>(col)[i] = v; break;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) gather_kernel(GatherCols g, const int32_t* __restrict__ idx, size_t n,
                                                           size_t in_rows, bool merge_valid) {
+  constexpr int U = 4;
   const size_t nbytes = (n + 7) / 8;
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t b = (size_t)blockIdx.x * kThreads + threadIdx.x; b < nbytes; b += stride) {
-    int32_t src[8];
+  const unsigned lane = threadIdx.x & 31u;
+  const size_t warps = (size_t)gridDim.x * (kThreads / 32);
+  const size_t groups = (n + 31) / 32;  // a group = 32 consecutive rows = 4 validity bytes
+  for (size_t g0 = (size_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); g0 < groups; g0 += warps * U) {
+    int32_t src[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const size_t i = b * 8 + j;
-      src[j] = i < n ? idx[i] : -1;
-      if (src[j] >= 0 && (size_t)src[j] >= in_rows) src[j] = -1;  // range-checked gather
+    for (int u = 0; u < U; ++u) {
+      const size_t grp = g0 + (size_t)u * warps, i = grp * 32 + lane;
+      src[u] = (grp < groups && i < n) ? idx[i] : -1;
+      if (src[u] >= 0 && (size_t)src[u] >= in_rows) src[u] = -1;  // range-checked gather
     }
 #pragma unroll 1
     for (int c = 0; c < g.ncols; ++c) {
-      unsigned vbits = 0;
+      const int width = g.width[c];
+      uint64_t val[U];
+      bool ok[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (src[j] < 0) continue;  // rows without a partner keep whatever the buffer held, bit stays 0
-        const size_t to = b * 8 + j, from = (size_t)src[j];
-        switch (g.width[c]) {
-          case 1: static_cast<uint8_t*>(g.out[c])[to] = static_cast<const uint8_t*>(g.in[c])[from]; break;
-          case 2: static_cast<uint16_t*>(g.out[c])[to] = static_cast<const uint16_t*>(g.in[c])[from]; break;
-          case 4: static_cast<uint32_t*>(g.out[c])[to] = static_cast<const uint32_t*>(g.in[c])[from]; break;
-          default: static_cast<uint64_t*>(g.out[c])[to] = static_cast<const uint64_t*>(g.in[c])[from]; break;
+      for (int u = 0; u < U; ++u) {
+        val[u] = 0;
+        ok[u] = false;
+        if (src[u] >= 0) {
+          val[u] = gather_load(g.in[c], width, (size_t)src[u]);
+          ok[u] = bit_valid(g.in_valid[c], (size_t)src[u]);
         }
-        if (bit_valid(g.in_valid[c], from)) vbits |= 1u << j;
       }
-      if (g.out_valid[c]) g.out_valid[c][b] = (gdf_valid_type)(merge_valid ? (g.out_valid[c][b] | vbits) : vbits);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t grp = g0 + (size_t)u * warps;
+        // rows without a partner keep whatever the buffer held, their bit stays 0
+        if (src[u] >= 0) gather_store(g.out[c], width, grp * 32 + lane, val[u]);
+        const unsigned bits = __ballot_sync(0xffffffffu, ok[u]);
+        const size_t byte = grp * 4 + lane;
+        if (g.out_valid[c] && lane < 4 && grp < groups && byte < nbytes) {
+          const gdf_valid_type v = (gdf_valid_type)((bits >> (8 * lane)) & 0xffu);
+          g.out_valid[c][byte] = merge_valid ? (gdf_valid_type)(g.out_valid[c][byte] | v) : v;
+        }
+      }
     }
   }
 }
@@ -493,7 +526,7 @@ gdf_error gather_columns(gdf_column* const* in_cols, gdf_column* const* out_cols
       g.out_valid[c] = oc->valid;
       g.width[c] = (unsigned char)w;
     }
-    gather_kernel<<<grid_for((n + 7) / 8), kThreads>>>(g, static_cast<const int32_t*>(indices->data), n,
+    gather_kernel<<<grid_for((n + 3) / 4), kThreads>>>(g, static_cast<const int32_t*>(indices->data), n,
                                                       in_cols[base]->size, merge_valid);
     B200_CHECK_LAST();
   }

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""ncu CSV logs (one per workload, `--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv`)
+-> profiles/r02_traffic_full_size.json: DRAM bytes per launch of every library kernel, grouped by bench.py workload key
+and by the timer name bench.py reports, together with the hash of the kernel sources they were captured from.
+Usage: python tools/traffic_from_ncu.py WORKLOAD=FILE.csv ... > profiles/r02_traffic_full_size.json"""
+import csv
+import json
+import os
+import re
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+# kernel function name (regex) -> bench.py timer name
+TIMER = [(r"probe32|part_probe", "join_part_probe"), (r"build32|part_build_kernel", "join_part_build"), (r"part_hist", "join_part_hist"),
+         (r"part_scatter", "join_part_scatter"), (r"fixup", "join_output_fixup"), (r"build_fast", "groupby_build_fast"),
+         (r"extract_fast", "groupby_extract"), (r"select_stream|select_chunked|select_kernel", "select"), (r"compare_static", "compare_static"),
+         (r"reduce_kernel", "reduce"), (r"binary_", "binary_op"), (r"partition_(hist|scan|scatter)_kernel", "hash_partition"),
+         (r"gather_kernel", "join_gather")]
+
+
+def main():
+    entries = {}
+    for arg in sys.argv[1:]:
+        key, path = arg.split("=", 1)
+        rows = [r for r in csv.reader(open(path)) if r]
+        hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r and "Metric Name" in r)
+        hdr = {h: i for i, h in enumerate(rows[hdr_i])}
+        per = {}   # (launch id, kernel) -> {metric: value}
+        for r in rows[hdr_i + 1:]:
+            if len(r) <= hdr["Metric Value"]:
+                continue
+            val, unit = float(r[hdr["Metric Value"]].replace(",", "")), r[hdr["Metric Unit"]]
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1, "us": 1e3, "ms": 1e6, "nsecond": 1, "usecond": 1e3, "msecond": 1e6}.get(unit, 1)
+            per.setdefault((r[hdr["ID"]], r[hdr["Kernel Name"]]), {})[r[hdr["Metric Name"]]] = val * scale
+        agg = {}
+        for (_, kname), m in per.items():
+            timer = next((t for pat, t in TIMER if re.search(pat, kname)), None)
+            if timer is None:
+                continue
+            a = agg.setdefault(timer, {"dram_read": 0.0, "dram_write": 0.0, "ncu_time_ns": 0.0, "launches": 0})
+            a["dram_read"] += m.get("dram__bytes_read.sum", 0)
+            a["dram_write"] += m.get("dram__bytes_write.sum", 0)
+            a["ncu_time_ns"] += m.get("gpu__time_duration.sum", 0)
+            a["launches"] += 1
+        # per LAUNCH of the timer's dominant kernel: timers that bracket several launches (two scatters) report the mean
+        entries[key] = {t: {"dram_read": int(a["dram_read"] / a["launches"]), "dram_write": int(a["dram_write"] / a["launches"]),
+                            "ncu_time_ns": int(a["ncu_time_ns"] / a["launches"]), "launches_in_capture": a["launches"]}
+                        for t, a in agg.items()}
+    json.dump({"_comment": "DRAM bytes per launch at FULL BASELINE size (ncu single-pass counters, one bench step per workload, "
+                           "tools/traffic_full.sh). bench.py reports roofline.traffic from here only while csrc_sha1 matches the sources.",
+               "csrc_sha1": bench.csrc_sha1(), "entries": entries}, sys.stdout, indent=1)
+
+
+if __name__ == "__main__":
+    main()
