@@ -32,7 +32,11 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr unsigned kMaxParts = 256;
-constexpr size_t kRowsPerPartition = 1u << 20;  // target build rows per partition (table <= 32 MB)
+// Target build rows per partition (8-byte slots: tables <= 16 MB).  2^19 was measured against it at C3 (shipped build):
+// probe 8.36 -> 7.82 ms (smaller tables hold on to L2 better while 124 MB of pairs and output stream past them), but
+// scatter 4.36 -> 5.05 ms (256 bins: 16-pair runs, twice the bulk stores per row) and build 3.17 -> 3.49 ms: step 17.95 ->
+// 18.10 ms.  At 2 GPUs the same change cost 1.7 ms in the exchange and bought nothing in the probe.
+constexpr int kRowsPerPartitionLog2 = 20;
 constexpr int kScatterRows = 16;                // rows per thread in the scatter tile
 constexpr int kScatterTile = kThreads * kScatterRows;
 constexpr int kBuildTile = kThreads * 8;
@@ -1638,7 +1642,8 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
   g.dest = 0;
   g.nlocal = 0;
   {
-    unsigned np = pow2_at_least((B + kRowsPerPartition - 1) / kRowsPerPartition);
+    const size_t rows_per_part = (size_t)1 << lab_knob("B200_ROWS_PER_PART_LOG2", kRowsPerPartitionLog2);
+    unsigned np = pow2_at_least((B + rows_per_part - 1) / rows_per_part);
     if (np > kMaxParts) np = kMaxParts;
     unsigned lg = 0;
     while ((1u << lg) < np) ++lg;
