@@ -449,6 +449,11 @@ probe32_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, unsigned lab)
 //     tile ever produces more stragglers than the queue holds, that tile falls back to resolving in place.)
 //   * INNER: output positions from per-warp chunks as described above, with a branch-free fast path for tiles that
 //     do not cross a chunk boundary.  LEFT / FULL: one pair per row at the row's own position.
+// PADDED layout (cap_tiles != 0; INNER joins with unique build keys): the probe side was partitioned WITHOUT a histogram
+// pass - partition p owns the fixed region [p * cap, (p + 1) * cap) of pr.pairs (cap = cap_tiles * 256 pairs) and
+// part_start[p] is the END of what the scatter wrote there.  A tile then never straddles partitions; tiles beyond a
+// region's end are empty and skipped, the last tile of a region is partial.  Because tiles can now be skipped, the
+// mbarrier phase of every ring stage is tracked explicitly (it flips only when a bulk copy was waited for).
 constexpr unsigned kQCap = 128;   // straggler queue entries per warp (power of two)
 
 struct Probe32USmem {
@@ -462,17 +467,24 @@ constexpr size_t probe32u_smem_bytes() {
   return (size_t)kC32Warps * kC32Stages * kC32Tile * sizeof(uint2) + sizeof(Probe32USmem) + 128;
 }
 
-template <bool LEFT_LIKE>
+template <bool LEFT_LIKE, bool PADDED>
 __global__ void __launch_bounds__(kC32Threads, 1)
 probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const unsigned long long* __restrict__ part_start,
-                      unsigned lab) {
+                      unsigned cap_tiles, unsigned lab) {
   extern __shared__ __align__(128) unsigned char probe32u_smem[];
   uint2* const ring_all = reinterpret_cast<uint2*>(probe32u_smem);
   Probe32USmem& sm = *reinterpret_cast<Probe32USmem*>(probe32u_smem + (size_t)kC32Warps * kC32Stages * kC32Tile * sizeof(uint2));
   const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-  const size_t tiles = (pr.n + kC32Tile - 1) / kC32Tile;
-  const size_t gw = (size_t)blockIdx.x * kC32Warps + warp;
-  const size_t W = (size_t)gridDim.x * kC32Warps;
+  // The kernel sits at the 128-register limit of a 512-thread CTA, and a spilled register costs far more than its
+  // instructions here: local-memory traffic does not fit the L1 left beside 170 KB of shared memory, reaches L2 and
+  // evicts the tables (ncu, first padded version: 24 bytes of spill -> +20 GB of L2 reads, table hit rate 83 % -> 52 %,
+  // 8.4 -> 13.4 ms).  The padded variant therefore keeps tile indices and output positions in 32 bits (tiles < 2^32;
+  // join outputs are int32-indexed, so positions < 2^32), the contiguous variant keeps the types it was tuned with.
+  using idx_t = typename std::conditional<PADDED, unsigned, size_t>::type;
+  using pos_t = typename std::conditional<PADDED, unsigned, unsigned long long>::type;
+  const idx_t tiles = (idx_t)((pr.n + kC32Tile - 1) / kC32Tile);
+  const idx_t gw = (idx_t)blockIdx.x * kC32Warps + warp;
+  const idx_t W = (idx_t)gridDim.x * kC32Warps;
   uint2* const ring = ring_all + (size_t)warp * kC32Stages * kC32Tile;
   uint64_t* const bar = sm.bar[warp];
   uint4* const queue = sm.queue[warp];
@@ -503,21 +515,30 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
   }
   __syncthreads();  // the only CTA-wide barrier
 
-  auto issue = [&](size_t it) {
-    const size_t tl = it * W + gw;
-    if (tl < tiles && (tl + 1) * kC32Tile <= pr.n) {
+  // rows of tile tl that exist: contiguous layout - everything up to pr.n; padded layout - up to the end of what the
+  // scatter wrote into the tile's partition region (32-bit arithmetic: tiles < 2^32)
+  auto tile_rows = [&](idx_t tl) -> unsigned {
+    if (tl >= tiles) return 0u;
+    const size_t row0 = (size_t)tl * kC32Tile;
+    const size_t end = PADDED ? (size_t)sm.part_start[(unsigned)tl / cap_tiles] : pr.n;
+    return end <= row0 ? 0u : (end - row0 >= (size_t)kC32Tile ? (unsigned)kC32Tile : (unsigned)(end - row0));
+  };
+  auto issue = [&](idx_t it) {  // lane 0: bulk copy of this warp's tile of iteration `it` (full tiles only)
+    const idx_t tl = it * W + gw;
+    if (PADDED ? tile_rows(tl) == (unsigned)kC32Tile : (tl < tiles && ((size_t)tl + 1) * kC32Tile <= pr.n)) {
       const int s = (int)(it % kC32Stages);
       tma::mbar_expect_tx(&bar[s], kC32Tile * (uint32_t)sizeof(uint2));
-      bulk_load_policy(ring + (size_t)s * kC32Tile, pr.pairs + tl * kC32Tile, kC32Tile * (uint32_t)sizeof(uint2), &bar[s],
+      bulk_load_policy(ring + (size_t)s * kC32Tile, pr.pairs + (size_t)tl * kC32Tile, kC32Tile * (uint32_t)sizeof(uint2), &bar[s],
                        pol_stream);
     }
   };
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kC32Stages; ++s) issue((size_t)s);
+    for (int s = 0; s < kC32Stages; ++s) issue((idx_t)s);
   }
+  unsigned phase_bits = 0;  // bit s = parity the next bulk copy into stage s completes
   const unsigned lt_mask = lanemask_lt();
-  unsigned long long chunk_base = 0, next_base = 0;
+  pos_t chunk_base = 0, next_base = 0;
   unsigned chunk_used = kC32Chunk;  // "no chunk yet"
   bool have_next = false;
   unsigned cur_p = 0;               // partition of the current tile's first pair (tiles of a warp only move forward)
@@ -543,23 +564,33 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
     return f >= 0 || (uint32_t)(b.w[3] >> 32) == 0xffffffffu;
   };
 
-  for (size_t it = 0;; ++it) {
-    const size_t tl = it * W + gw;
-    const bool has_tile = tl < tiles;
-    if (!has_tile && q_count == 0) break;   // after the last tile: extra iterations drain the queue
-    const size_t row0 = tl * kC32Tile;
-    const bool full = has_tile && row0 + kC32Tile <= pr.n;
+  for (idx_t it = 0;; ++it) {
+    const idx_t tl = it * W + gw;
+    const unsigned rows_here = PADDED ? tile_rows(tl) : 0u;
+    const bool has_tile = PADDED ? rows_here != 0 : tl < tiles;
+    if (PADDED ? (tl >= tiles && q_count == 0) : (!has_tile && q_count == 0)) break;   // after the last tile: extra iterations drain the queue
+    const size_t row0 = (size_t)tl * kC32Tile;
+    const bool full = PADDED ? rows_here == (unsigned)kC32Tile : (has_tile && row0 + kC32Tile <= pr.n);
     const int s = (int)(it % kC32Stages);
+    if (PADDED && !has_tile && q_count == 0) {  // an empty tile of the padded layout (warp-uniform): nothing was copied for it
+      if (lane == 0) issue(it + kC32Stages);
+      continue;
+    }
     if (!LEFT_LIKE && !have_next && chunk_used + (kC32Tile + 32) > kC32Chunk) {
       // the tile (+ up to 32 queued rows) may overflow the current chunk: ask for the next one now, use it later
-      if (lane == 0) next_base = atomicAdd(out.cursor, (unsigned long long)kC32Chunk);
+      if (lane == 0) next_base = (pos_t)atomicAdd(out.cursor, (unsigned long long)kC32Chunk);
       have_next = true;
     }
     bool one_part = false;
     unsigned off_u = 0, mask_u = 0;
     if (has_tile) {
-      while (row0 >= sm.part_start[cur_p + 1]) ++cur_p;
-      one_part = (full ? row0 + kC32Tile : pr.n) <= sm.part_start[cur_p + 1];
+      if (PADDED) {
+        cur_p = (unsigned)tl / cap_tiles;
+        one_part = true;
+      } else {
+        while (row0 >= sm.part_start[cur_p + 1]) ++cur_p;
+        one_part = (full ? row0 + kC32Tile : pr.n) <= sm.part_start[cur_p + 1];
+      }
       off_u = sm.part_off[cur_p];
       mask_u = sm.part_mask[cur_p];
     }
@@ -568,13 +599,15 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
     // is handed back to the producer at the end of the iteration; three other stages are in flight meanwhile.
     uint2* const stage = ring + (size_t)s * kC32Tile;
     if (full) {
-      tma::mbar_wait(&bar[s], (unsigned)(it / kC32Stages) & 1u);
-    } else {  // ragged last tile / queue-draining iteration: no bulk copy was issued for this stage
+      // contiguous layout: every earlier use of the stage was a bulk copy, so the phase follows from the iteration number
+      tma::mbar_wait(&bar[s], PADDED ? ((phase_bits >> s) & 1u) : ((unsigned)(it / kC32Stages) & 1u));
+      if (PADDED) phase_bits ^= 1u << s;
+    } else {  // partial tile / queue-draining iteration: no bulk copy was issued for this stage
 #pragma unroll
       for (int i = 0; i < kC32Rows; ++i) {
         const size_t j = row0 + i * 32 + lane;
         uint2 v = make_uint2(0u, 0x80000000u);  // no row here: tag INT_MIN
-        if (has_tile && j < pr.n) v = pr.pairs[j];
+        if (PADDED ? ((unsigned)(i * 32 + lane) < rows_here) : (has_tile && j < pr.n)) v = pr.pairs[j];
         stage[i * 32 + lane] = v;
       }
       __syncwarp();
@@ -711,8 +744,8 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
         }
       } else {  // split: the first in_old pairs finish the current chunk, the rest start the next one
         const unsigned in_old = kC32Chunk - chunk_used;
-        const unsigned long long old_at = chunk_base + chunk_used;
-        const unsigned long long new_base = __shfl_sync(0xffffffffu, next_base, 0);
+        const pos_t old_at = chunk_base + chunk_used;
+        const pos_t new_base = __shfl_sync(0xffffffffu, next_base, 0);
         chunk_base = new_base;
         chunk_used = total - in_old;
         have_next = false;
@@ -733,7 +766,7 @@ probe32_unique_kernel(Pairs32 pr, PartGeom g, Tables32 t, Probe32Out out, const 
     }
     // ---- every lane is done with the stage: hand it back to the producer ----
     __syncwarp();
-    if (full && lane == 0) {
+    if ((PADDED || full) && lane == 0) {  // padded: also after a partial tile - its stage was written with ordinary stores
       tma::fence_proxy_async();
       issue(it + kC32Stages);
     }

@@ -266,3 +266,26 @@ def test_compact_path_heavy_duplicates():
     assert np.array_equal(probe[gl], build[gr])
     pairs = gl.astype(np.int64) * nb + gr
     assert len(np.unique(pairs)) == len(pairs)
+
+
+# ---- histogram-free probe side of the compact INNER path (fixed partition regions + overflow fallback) ----
+@pytest.mark.parametrize("np_rows", [1_048_576, 3_000_017, 5_250_000])
+def test_padded_probe_layout_uniform_keys(np_rows):
+    """INNER, unique 32-bit build keys, >= 2^20 probe rows: the probe side is partitioned without a histogram pass into
+    fixed regions; region ends, partial and empty tiles are exercised by sizes that do not divide anything."""
+    nb = 1_300_000
+    build = np.random.permutation(nb).astype(np.int64)
+    probe = np.random.randint(0, 2 * nb, np_rows).astype(np.int64)
+    check("inner", [probe], [build])
+
+
+@pytest.mark.parametrize("hot", [0.2, 0.9])
+def test_padded_probe_layout_overflows_on_skewed_keys_and_falls_back(hot):
+    """A hot probe key overflows its partition's region: the scatter drops what does not fit (raising a flag, never
+    writing out of bounds), the partial result is discarded and the side is partitioned again with exact counts."""
+    nb, npr = 2_200_000, 4_000_000
+    build = np.random.permutation(nb).astype(np.int64)
+    probe = np.random.randint(0, nb, npr).astype(np.int64)
+    probe[np.random.rand(npr) < hot] = 12345
+    check("inner", [probe], [build])
+    check("inner", [build], [probe[:1_100_000]])      # flipped sizes: the hot key is now on the build side (duplicates -> exact path)
