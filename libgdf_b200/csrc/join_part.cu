@@ -1469,6 +1469,13 @@ __global__ void table_meta_kernel(const TableMeta m, unsigned long long* __restr
   }
 }
 
+// The library's private non-blocking stream: table builds that run beside a scatter on the legacy stream.
+static cudaStream_t xjoin_side_stream() {
+  static cudaStream_t s = nullptr;
+  if (s == nullptr && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+  return s;
+}
+
 // Stage 1 of the compact join: size, initialise and fill the per-partition tables, all on stream `s` (the legacy stream
 // for a single-GPU join; a private stream when the multi-GPU layer overlaps it with the probe side's exchange).
 gdf_error compact_build(PartGeom g, const Pairs32& bp, const unsigned long long* h_btot, unsigned long long* d_toffset,
@@ -1700,27 +1707,56 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
       e = partition_scatter32<KT, false>(build_col, g, h_cursors, d_cursors, bpairs.as<uint2>(), build_payload, 0);
       if (e != GDF_SUCCESS) return e;
       const Pairs32 bp32{bpairs.as<uint2>(), kept};
-      // tables first: whether the build keys are unique decides how the probe side is partitioned
+      // INNER join with a plain probe column: NO histogram pass over the probe side, and the tables are filled on a
+      // private stream WHILE the probe side is scattered (the build is bound by DRAM-cold random sector reads at low
+      // occupancy, the scatter by the LSU and bandwidth: they overlap well; the scatter runs at 2 CTAs per SM so that a
+      // build CTA fits beside it).  Partition p gets the fixed region [p * cap, (p + 1) * cap) of the pair array (cap =
+      // the even share + 1/16 + 4096 pairs), the scatter's cursors start at the region starts, the probe kernel reads the
+      // region ends from the cursors (device to device) and skips the padding.  Both shortcuts are optimistic: if the
+      // build keys turn out to have duplicates (the count / cursor probe kernels need the contiguous layout) or a
+      // skewed probe column overflows a region (the run is dropped and flagged, never written out of bounds), the
+      // probe side is partitioned again with exact counts.  C3: 17.9 -> 15.7 ms (no histogram) -> see DESIGN.md.
+      bool padded = kind == JOIN_INNER && probe_col->valid == nullptr && probe_payload == nullptr && P >= (1u << 20) &&
+                    lab_knob("B200_PADDED_PROBE", 1) != 0;
+      const bool overlap = padded && lab_knob("B200_BUILD_OVERLAP", 1) != 0 && xjoin_side_stream() != nullptr;
       Scratch table;
       Tables32 t{nullptr, nullptr, nullptr};
-      {
+      cudaEvent_t built = nullptr;
+      if (overlap) {
+        cudaStream_t side = xjoin_side_stream();
+        cudaEvent_t issued = nullptr;
+        B200_CUDA_TRY(cudaEventCreateWithFlags(&issued, cudaEventDisableTiming));
+        cudaError_t ce = cudaEventRecord(issued, 0);   // the private stream starts after the build side's scatter
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(side, issued, 0);
+        cudaEventDestroy(issued);
+        if (ce != cudaSuccess) return GDF_CUDA_ERROR;
+        e = compact_build(g, bp32, h_btot, d_toffset, d_tmask, d_flags, table, &t, side);
+        if (e == GDF_SUCCESS && (cudaEventCreateWithFlags(&built, cudaEventDisableTiming) != cudaSuccess ||
+                                 cudaEventRecord(built, side) != cudaSuccess))
+          e = GDF_CUDA_ERROR;
+        if (e != GDF_SUCCESS) {
+          cudaStreamSynchronize(side);
+          if (built) cudaEventDestroy(built);
+          return e;
+        }
+      } else {
         B200_TIMED("join_part_build");
         e = compact_build(g, bp32, h_btot, d_toffset, d_tmask, d_flags, table, &t, 0);
         if (e != GDF_SUCCESS) return e;
       }
       *handled = true;
-      // INNER join, unique build keys, plain probe column: NO histogram pass over the probe side.  Partition p gets the
-      // fixed region [p * cap, (p + 1) * cap) of the pair array (cap = the even share + 1/16 + 4096 pairs), the scatter's
-      // cursors start at the region starts, the probe kernel reads the region ends from the cursors (device to device)
-      // and skips the padding.  Saves the 8 GB read of C3's probe histogram (1.4 of 18 ms).  A probe column skewed
-      // enough to overflow a region raises a flag (the run is dropped, never written out of bounds); the side is then
-      // partitioned again with exact counts.
-      bool padded = kind == JOIN_INNER && probe_col->valid == nullptr && probe_payload == nullptr && P >= (1u << 20) &&
-                    lab_knob("B200_PADDED_PROBE", 1) != 0;
-      if (padded) {
-        int h_flags[2] = {0, 0};
+      // everything below that returns early must first make the legacy stream wait for the private one
+      auto join_streams = [&]() -> gdf_error {
+        if (built == nullptr) return GDF_SUCCESS;
+        const cudaError_t ce = cudaStreamWaitEvent(0, built, 0);
+        cudaEventDestroy(built);
+        built = nullptr;
+        return ce == cudaSuccess ? GDF_SUCCESS : GDF_CUDA_ERROR;
+      };
+      int h_flags[2] = {0, 0};
+      if (padded && !overlap) {
         B200_CUDA_TRY(cudaMemcpy(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
-        if (h_flags[0] != 0) padded = false;  // duplicate build keys: the count / cursor probe kernels need the contiguous layout
+        if (h_flags[0] != 0) padded = false;  // duplicate build keys
       }
       if (padded) {
         const size_t share = (P + g.nparts - 1) / g.nparts;
@@ -1736,23 +1772,42 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
         reg.overflow = d_overflow;
         for (int r = 0; r < kMaxPeers; ++r) reg.base[r] = nullptr;
         reg.base[0] = ppairs.as<uint2>();
-        e = partition_scatter32<KT, false>(probe_col, g, h_cursors, d_cursors, ppairs.as<uint2>(), nullptr, 0, &reg);
-        if (e != GDF_SUCCESS) return e;
+        e = partition_scatter32<KT, false>(probe_col, g, h_cursors, d_cursors, ppairs.as<uint2>(), nullptr, 0, &reg, false,
+                                           overlap ? lab_knob("B200_OVERLAP_SCATTER_CTAS", 2) : 0);
+        if (e == GDF_SUCCESS) e = join_streams();
+        if (e != GDF_SUCCESS) {
+          cudaDeviceSynchronize();
+          if (built) cudaEventDestroy(built);
+          return e;
+        }
         // region ends = the cursors after the scatter; [nparts] is not read in this layout
         B200_CUDA_TRY(cudaMemcpyAsync(d_pstart, d_cursors, g.nparts * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, 0));
-        const Pairs32 pp32{ppairs.as<uint2>(), (size_t)g.nparts * cap};
-        e = compact_probe(kind, flip, g, t, pp32, B, d_cursor, d_flags, d_pstart, out_l, out_r, (unsigned)(cap / kC32Tile), P);
-        if (e != GDF_SUCCESS) return e;
-        int overflow = 0;
-        B200_CUDA_TRY(cudaMemcpy(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
-        if (!overflow) return GDF_SUCCESS;
-        // skewed probe keys: discard the partial result, fall through to the exact path
-        if (out_l->data) rmmFree(out_l->data, 0);
-        if (out_r->data) rmmFree(out_r->data, 0);
-        view_indices(out_l, nullptr, 0);
-        view_indices(out_r, nullptr, 0);
+        bool redo = false;
+        if (overlap) {  // the build ran beside the scatter: only now are its flags known
+          B200_CUDA_TRY(cudaMemcpy(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
+          redo = h_flags[0] != 0;
+        }
+        if (!redo) {
+          const Pairs32 pp32{ppairs.as<uint2>(), (size_t)g.nparts * cap};
+          e = compact_probe(kind, flip, g, t, pp32, B, d_cursor, d_flags, d_pstart, out_l, out_r, (unsigned)(cap / kC32Tile), P);
+          if (e != GDF_SUCCESS) return e;
+          int overflow = 0;
+          B200_CUDA_TRY(cudaMemcpy(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+          if (!overflow) return GDF_SUCCESS;
+          // skewed probe keys: discard the partial result, fall through to the exact path
+          if (out_l->data) rmmFree(out_l->data, 0);
+          if (out_r->data) rmmFree(out_r->data, 0);
+          view_indices(out_l, nullptr, 0);
+          view_indices(out_r, nullptr, 0);
+        }
         ppairs.release();
-        B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 64, 0));
+        // cursor, overflow flag and ticket start again; the duplicate flag (first int after the cursor) is kept
+        B200_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), 0));
+        B200_CUDA_TRY(cudaMemsetAsync(d_cursor + 2, 0, 64 - 2 * sizeof(unsigned long long), 0));
+      }
+      {
+        const gdf_error je = join_streams();
+        if (je != GDF_SUCCESS) return je;
       }
       e = left_like ? partition_hist<KT, true, true>(probe_col, g, d_totals, h_ptot)
                     : partition_hist<KT, false, true>(probe_col, g, d_totals, h_ptot);
@@ -2116,12 +2171,6 @@ struct XJoinHandle {
   cudaEvent_t done = nullptr;
   bool side = false;
 };
-
-static cudaStream_t xjoin_side_stream() {
-  static cudaStream_t s = nullptr;
-  if (s == nullptr && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
-  return s;
-}
 
 gdf_error xjoin_build(const void* build_pairs, const unsigned long long* build_counts, unsigned nlocal, bool side, void** handle) {
   B200_REQUIRE(nlocal >= 1 && nlocal <= kMaxParts && (nlocal & (nlocal - 1)) == 0, GDF_INVALID_API_CALL);
