@@ -74,12 +74,18 @@ gdf_error gdfx_peer_free(void *ptr);
  *   gdfx_xjoin_count    counts[r * nlocal + p] (host) = rows of `key` going to (rank r, local partition p);
  *                       *hi_or = OR of the keys' high words
  *   gdfx_xjoin_scatter  dst_pairs[r] = rank r's pair buffer as mapped on this device (gdfx_peer_open), 8 bytes per
- *                       pair; dst_offsets[r * nlocal + p] (host) = where this rank's pairs of that bin start
+ *                       pair; dst_offsets[r * nlocal + p] (host) = where this rank's pairs of that bin start; counts =
+ *                       what gdfx_xjoin_count returned.  LAYOUT: every (sender, bin) slot of a receive buffer holds an
+ *                       whole number of 32-byte granules (4 pairs) - the rest of a slot is padded with {0, INT_MIN} "no
+ *                       row" pairs, which the local join skips - so that only sector-aligned bulk stores cross NVLink
+ *                       (8-byte peer stores halve its throughput, partial sectors cost 10-30 %,
+ *                       profiles/r02_p2p_store_bench.txt); offsets and per-partition totals are those of the padded
+ *                       slots (dist.plan_fused_exchange / gdfx_xjoin_plan_dev do the rounding)
  *   gdfx_xjoin_local    INNER join of this rank's received pairs; *_counts[p] (host) = pairs of local partition p
  *                       (summed over the senders); outputs hold the travelling ids, as gdfx_join_pairs */
 gdf_error gdfx_xjoin_count(gdf_column *key, int ranks, int nlocal, unsigned long long *counts, unsigned *hi_or);
 gdf_error gdfx_xjoin_scatter(gdf_column *key, int32_t id_base, int ranks, int nlocal, void * const *dst_pairs,
-                             const unsigned long long *dst_offsets);
+                             const unsigned long long *dst_offsets, const unsigned long long *counts);
 /* The same exchange WITHOUT host round trips between the histogram and the scatter: counts stay on the device
  * (d_counts[ranks * nlocal + 1]: the bins, then the OR of the keys' high words), the caller all-gathers
  * {build counts | probe counts} of every rank into d_all[ranks][2 * (ranks * nlocal + 1)], gdfx_xjoin_plan_dev turns
@@ -93,7 +99,8 @@ gdf_error gdfx_xjoin_plan_dev(const unsigned long long *d_all, int ranks, int nl
                               unsigned long long cap_probe, unsigned long long *d_off_build, unsigned long long *d_off_probe,
                               int *d_status);
 gdf_error gdfx_xjoin_scatter_dev(gdf_column *key, int32_t id_base, int ranks, int nlocal, void * const *dst_pairs,
-                                 const unsigned long long *d_offsets, const int *d_status, int ctas_per_sm);
+                                 const unsigned long long *d_offsets, const unsigned long long *d_counts, const int *d_status,
+                                 int ctas_per_sm);
 /* gdfx_xjoin_local in two stages, so that a rank fills its hash tables WHILE the probe side is still crossing NVLink:
  * gdfx_xjoin_build is ordered after everything issued so far on the legacy stream (i.e. after the build side's
  * exchange) and, with overlap != 0, runs on a private non-blocking stream; gdfx_xjoin_probe makes the legacy stream wait

@@ -47,7 +47,7 @@ gdf_error partition_scatter_peer(const gdf_column* key, int32_t id_base, unsigne
                                  int32_t* const* dst_ids, const unsigned long long* dst_offsets);
 gdf_error xjoin_count(const gdf_column* key, unsigned ranks, unsigned nlocal, unsigned long long* h_counts, unsigned* hi_or);
 gdf_error xjoin_scatter(const gdf_column* key, int32_t id_base, unsigned ranks, unsigned nlocal, void* const* dst_pairs,
-                        const unsigned long long* h_offsets, const int* d_status, int ctas_per_sm);
+                        const unsigned long long* offsets, const unsigned long long* counts, const int* d_status, int ctas_per_sm);
 gdf_error xjoin_build(const void* build_pairs, const unsigned long long* build_counts, unsigned nlocal, bool side, void** handle);
 gdf_error xjoin_probe(void* handle, const void* probe_pairs, const unsigned long long* probe_counts, gdf_column* out_l,
                       gdf_column* out_r);
@@ -748,13 +748,13 @@ extern "C" gdf_error gdfx_xjoin_count(gdf_column* key, int ranks, int nlocal, un
   return xjoin_count(key, (unsigned)ranks, (unsigned)nlocal, counts, hi_or);
 }
 extern "C" gdf_error gdfx_xjoin_scatter(gdf_column* key, int32_t id_base, int ranks, int nlocal, void* const* dst_pairs,
-                                        const unsigned long long* dst_offsets) {
-  B200_REQUIRE(key && dst_pairs && dst_offsets, GDF_DATASET_EMPTY);
+                                        const unsigned long long* dst_offsets, const unsigned long long* counts) {
+  B200_REQUIRE(key && dst_pairs && dst_offsets && counts, GDF_DATASET_EMPTY);
   B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
   B200_REQUIRE(key->size < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
   B200_REQUIRE(ranks >= 1 && nlocal >= 1, GDF_INVALID_API_CALL);
   if (key->size == 0) return GDF_SUCCESS;
-  return xjoin_scatter(key, id_base, (unsigned)ranks, (unsigned)nlocal, dst_pairs, dst_offsets, nullptr, 0);
+  return xjoin_scatter(key, id_base, (unsigned)ranks, (unsigned)nlocal, dst_pairs, dst_offsets, counts, nullptr, 0);
 }
 // the local join in two stages: tables are filled on a private stream while the probe side is still being exchanged
 extern "C" gdf_error gdfx_xjoin_build(const void* build_pairs, const unsigned long long* build_counts, int nlocal, int overlap,
@@ -784,13 +784,14 @@ extern "C" gdf_error gdfx_xjoin_plan_dev(const unsigned long long* d_all, int ra
                         d_status);
 }
 extern "C" gdf_error gdfx_xjoin_scatter_dev(gdf_column* key, int32_t id_base, int ranks, int nlocal, void* const* dst_pairs,
-                                            const unsigned long long* d_offsets, const int* d_status, int ctas_per_sm) {
-  B200_REQUIRE(key && dst_pairs && d_offsets && d_status, GDF_DATASET_EMPTY);
+                                            const unsigned long long* d_offsets, const unsigned long long* d_counts,
+                                            const int* d_status, int ctas_per_sm) {
+  B200_REQUIRE(key && dst_pairs && d_offsets && d_counts && d_status, GDF_DATASET_EMPTY);
   B200_REQUIRE(key->valid == nullptr, GDF_VALIDITY_UNSUPPORTED);
   B200_REQUIRE(key->size < 0x7fffffffull, GDF_COLUMN_SIZE_TOO_BIG);
   B200_REQUIRE(ranks >= 1 && nlocal >= 1, GDF_INVALID_API_CALL);
   if (key->size == 0) return GDF_SUCCESS;
-  return xjoin_scatter(key, id_base, (unsigned)ranks, (unsigned)nlocal, dst_pairs, d_offsets, d_status, ctas_per_sm);
+  return xjoin_scatter(key, id_base, (unsigned)ranks, (unsigned)nlocal, dst_pairs, d_offsets, d_counts, d_status, ctas_per_sm);
 }
 extern "C" gdf_error gdfx_xjoin_local(const void* probe_pairs, const unsigned long long* probe_counts, const void* build_pairs,
                                       const unsigned long long* build_counts, int nlocal, gdf_column* out_l, gdf_column* out_r) {

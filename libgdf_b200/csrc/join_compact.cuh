@@ -94,7 +94,7 @@ build32_kernel(Pairs32 b, PartGeom g, Tables32 t, int* __restrict__ flags /*[0]=
     at[u] = 0;
     mask[u] = 3;
     taken[u] = 0;
-    if (i < b.n) {
+    if (i < b.n && b.pairs[i].y != 0x80000000u) {  // tag INT_MIN = the exchange's "no row" pad pair
       const uint2 pr = b.pairs[i];
       mine[u] = ((unsigned long long)pr.y << 32) | pr.x;
       const uint32_t h = KeyBits<uint32_t>::hash(pr.x);

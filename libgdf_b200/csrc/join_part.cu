@@ -380,6 +380,10 @@ struct PeerPairs {
   // end is dropped and *overflow is raised (the caller then repeats the side with exact counts)
   unsigned long long region_cap;
   int* overflow;
+  // multi-GPU exchange (part_scatter32_even_kernel): this rank's rows per bin and its start offset inside the
+  // destinations' buffers (device arrays); every (sender, bin) slot there holds even(count) pairs
+  const unsigned long long* counts;
+  const unsigned long long* offsets0;
 };
 
 template <typename KT, bool KEEP_NULLS>
@@ -585,6 +589,146 @@ part_scatter32_bulk_kernel(const KT* __restrict__ keys, size_t n, PartGeom g, un
         if (len & 1u) dst[body] = src[body];
         tma::bulk_commit();
       }
+    }
+  }
+  tma::bulk_wait_all();
+}
+
+// ---- the exchange's scatter: SECTOR-ALIGNED runs only ----
+// tools/p2p_bench.cu (profiles/r02_p2p_store_bench.txt): NVLink is bound by the NUMBER of write packets, not by bytes.
+// One plain 8-byte peer store next to every 256-byte bulk store takes it from 695 to 487 GB/s, two take it to 394 (the
+// odd head / tail pairs of part_scatter32_bulk_kernel were exactly such packets: the exchange measured 0.42 TB/s); a bulk
+// store that starts or ends inside a 32-byte sector costs too (256-byte runs: 700 GB/s aligned, 618 at 32-byte, 497 at
+// 16-byte alignment).  Here nothing but whole-sector bulk stores leaves the SM in the steady state:
+//   * the receiver's layout gives every (sender, bin) slot a length that is a multiple of kXG = 4 pairs = 32 bytes (the
+//     plan rounds counts up, dist.py plan_fused_exchange / xjoin_plan_kernel), so a sender's cursor for a bin starts
+//     sector-aligned and - because every tile reserves a multiple of kXG pairs - stays so;
+//   * the up to kXG - 1 pairs of a bin that a tile cannot emit are CARRIED in shared memory into the CTA's next tile
+//     (staged first there);
+//   * what is still carried when the CTA runs out of tiles is written with single stores (<= 3 per bin and CTA, once,
+//     filling the slot from its back so that the front cursor other CTAs still use stays aligned), and CTA 0 fills the
+//     rest of every slot with {0, INT_MIN} "no row" pairs, which build and probe skip.
+constexpr unsigned kXG = 4;   // pairs per exchange granule (one 32-byte sector); dist.py EXCHANGE_GRANULE must agree
+
+struct Scatter32EvenSmem {
+  uint2 pairs[kS32Tile + 2 * (kXG - 1) * kMaxParts];
+  uint2 carry[kMaxParts][kXG - 1];
+  unsigned carried[kMaxParts];   // 0 .. kXG - 1
+  unsigned hist[2][kMaxParts];
+  unsigned lstart[kMaxParts];
+  unsigned long long gbase[kMaxParts];
+};
+
+template <typename KT>
+__global__ void __launch_bounds__(kS32Threads, 3)
+part_scatter32_even_kernel(const KT* __restrict__ keys, size_t n, PartGeom g, unsigned long long* __restrict__ cursors,
+                           int32_t id_base, const PeerPairs peer, const unsigned long long* __restrict__ counts,
+                           const unsigned long long* __restrict__ offsets0, unsigned* __restrict__ tail_cursors) {
+  extern __shared__ __align__(128) unsigned char scatter32e_smem[];
+  Scatter32EvenSmem& sm = *reinterpret_cast<Scatter32EvenSmem*>(scatter32e_smem);
+  if (peer.status != nullptr && (peer.status[0] | peer.status[1]) != 0) return;  // the device-side plan said "do not write"
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const size_t tiles = (n + kS32Tile - 1) / kS32Tile;
+  for (unsigned p = threadIdx.x; p < 2 * kMaxParts; p += kS32Threads) (&sm.hist[0][0])[p] = 0;
+  for (unsigned p = threadIdx.x; p < kMaxParts; p += kS32Threads) sm.carried[p] = 0;
+  if (blockIdx.x == 0)  // pad every slot up to a whole granule: "no row" pairs behind this rank's pairs of the bin
+    for (unsigned p = threadIdx.x; p < g.nparts; p += kS32Threads) {
+      const unsigned long long c = counts[p], end = (c + kXG - 1) & ~(unsigned long long)(kXG - 1);
+      for (unsigned long long i = c; i < end; ++i) peer.base[p >> peer.shift][offsets0[p] + i] = make_uint2(0u, 0x80000000u);
+    }
+  __syncthreads();
+  unsigned buf = 0;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1u) {
+    const size_t wbase = tile * kS32Tile + (size_t)warp * (32 * kS32Rows);
+    uint32_t k[kS32Rows];
+    unsigned wide = 0;
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      const size_t r = wbase + (size_t)i * 32 + lane;
+      const KT kk = r < n ? keys[r] : (KT)0;
+      k[i] = (uint32_t)kk;
+      if (sizeof(KT) == 8 && (uint32_t)((unsigned long long)kk >> 32) != 0) wide |= 1u << i;
+    }
+    unsigned rp[kS32Rows];  // rank << 16 | bin, 0xffff = dropped (past the end / key wider than 32 bits: it cannot match)
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      const size_t r = wbase + (size_t)i * 32 + lane;
+      const bool keep = r < n && !((wide >> i) & 1u);
+      const unsigned p = keep ? g.pid(KeyBits<uint32_t>::hash(k[i])) : 0u;
+      rp[i] = keep ? ((atomicAdd(&sm.hist[buf][p], 1u) << 16) | p) : 0xffffu;
+    }
+    __syncthreads();  // (1) tile histogram complete
+    {
+      const unsigned p = threadIdx.x;
+      if (p < g.nparts) {
+        const unsigned have = sm.hist[buf][p] + sm.carried[p];   // the carried pairs are staged first
+        const unsigned emit = have & ~(kXG - 1);
+        sm.gbase[p] = emit ? atomicAdd(&cursors[p], (unsigned long long)emit) : 0ull;
+        tma::bulk_wait_read_all();  // this thread's bulk store of the previous tile has finished reading shared memory
+      }
+      if (p < kMaxParts) sm.hist[buf ^ 1u][p] = 0;  // the other buffer, for the next tile
+    }
+    __syncthreads();  // (2a) reserved positions known, the previous tile's staged pairs are free
+    if (warp == kS32Threads / 32 - 1) {  // slot starts: exclusive scan of the slot lengths rounded up to granules (8 bins per lane)
+      unsigned c[kMaxParts / 32], tot = 0;
+#pragma unroll
+      for (int j = 0; j < (int)(kMaxParts / 32); ++j) {
+        const unsigned p = lane * (kMaxParts / 32) + j;
+        c[j] = p < g.nparts ? ((sm.hist[buf][p] + sm.carried[p] + kXG - 1) & ~(kXG - 1)) : 0;
+        tot += c[j];
+      }
+      unsigned inc = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += o;
+      }
+      unsigned run = inc - tot;
+#pragma unroll
+      for (int j = 0; j < (int)(kMaxParts / 32); ++j) {
+        const unsigned p = lane * (kMaxParts / 32) + j;
+        if (p < g.nparts) sm.lstart[p] = run;
+        run += c[j];
+      }
+    }
+    __syncthreads();  // (2b) slot starts visible
+    if (threadIdx.x < g.nparts)
+      for (unsigned i = 0; i < sm.carried[threadIdx.x]; ++i) sm.pairs[sm.lstart[threadIdx.x] + i] = sm.carry[threadIdx.x][i];
+#pragma unroll
+    for (int i = 0; i < kS32Rows; ++i) {
+      if ((rp[i] & 0xffffu) == 0xffffu) continue;
+      const unsigned p = rp[i] & 0xffffu;
+      const size_t row = wbase + (size_t)i * 32 + lane;
+      sm.pairs[sm.lstart[p] + sm.carried[p] + (rp[i] >> 16)] = make_uint2(k[i], (uint32_t)((int32_t)row + id_base));
+    }
+    tma::fence_proxy_async();  // the staged pairs are read by the copy engine
+    __syncthreads();           // (3) staged tile complete
+    {
+      const unsigned p = threadIdx.x;
+      if (p < g.nparts) {
+        const unsigned have = sm.hist[buf][p] + sm.carried[p];
+        const unsigned emit = have & ~(kXG - 1), rest = have & (kXG - 1);
+        const uint2* src = &sm.pairs[sm.lstart[p]];
+        if (emit) {
+          tma::bulk_store(peer.base[p >> peer.shift] + sm.gbase[p], src, emit * (unsigned)sizeof(uint2));
+          tma::bulk_commit();
+        }
+        for (unsigned i = 0; i < rest; ++i) sm.carry[p][i] = src[emit + i];  // not part of the bulk store's range
+        sm.carried[p] = rest;
+      }
+    }
+    // the next tile's barriers order these writes of carry / carried before their next readers
+  }
+  __syncthreads();
+  // What is still carried: single stores, <= kXG - 1 per bin and CTA.  They fill the slot from its BACK (just before the
+  // pad pairs), so that the front cursor - still used by other CTAs' bulk stores - stays sector-aligned; the runs and
+  // the singles meet exactly, because the slot holds the count rounded up to a granule.
+  if (threadIdx.x < g.nparts) {
+    const unsigned p = threadIdx.x, rest = sm.carried[p];
+    if (rest) {
+      const unsigned long long last_real = offsets0[p] + counts[p] - 1ull;   // the pads sit right behind it
+      const unsigned at = atomicAdd(&tail_cursors[p], rest);
+      for (unsigned i = 0; i < rest; ++i) peer.base[p >> peer.shift][last_real - (at + i)] = sm.carry[p][i];
     }
   }
   tma::bulk_wait_all();
@@ -1268,6 +1412,8 @@ gdf_error partition_scatter32(const gdf_column* col, PartGeom g, const unsigned 
   peer.status = nullptr;
   peer.region_cap = 0;
   peer.overflow = nullptr;
+  peer.counts = nullptr;
+  peer.offsets0 = nullptr;
   for (int r = 0; r < kMaxPeers; ++r) peer.base[r] = nullptr;
   if (peer_dst) peer = *peer_dst;
   const KT* keys = static_cast<const KT*>(col->data);
@@ -1294,7 +1440,21 @@ gdf_error partition_scatter32(const gdf_column* col, PartGeom g, const unsigned 
     peer.shift = 8;  // bin >> 8 == 0: everything goes to base[0]
     peer.base[0] = out_pairs;
   }
-  if (peer.on && !KEEP_NULLS && col->valid == nullptr && payload == nullptr) {  // the fused exchange: TMA bulk stores per bin
+  if (peer.on && peer.counts != nullptr && !KEEP_NULLS && col->valid == nullptr && payload == nullptr) {
+    // the multi-GPU exchange: even runs only (no 8-byte peer stores in the steady state)
+    auto ekern = part_scatter32_even_kernel<KT>;
+    const size_t esmem = sizeof(Scatter32EvenSmem);
+    B200_CUDA_TRY(cudaFuncSetAttribute(ekern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    int eper_sm = 1;
+    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eper_sm, ekern, kS32Threads, esmem));
+    if (ctas_per_sm > 0 && ctas_per_sm < eper_sm) eper_sm = ctas_per_sm;
+    const size_t ecap = (size_t)sm_count() * (size_t)(eper_sm > 0 ? eper_sm : 1);
+    const int eblocks = (int)(tiles < ecap ? (tiles ? tiles : 1) : ecap);
+    unsigned* d_tail = reinterpret_cast<unsigned*>(d_cursors + g.nparts);   // the caller's scratch holds 2 x nparts cells
+    B200_CUDA_TRY(cudaMemsetAsync(d_tail, 0, g.nparts * sizeof(unsigned), 0));
+    B200_TIMED("join_part_scatter");
+    ekern<<<eblocks, kS32Threads, esmem>>>(keys, n, g, d_cursors, id_base, peer, peer.counts, peer.offsets0, d_tail);
+  } else if (peer.on && !KEEP_NULLS && col->valid == nullptr && payload == nullptr) {  // single destination: TMA bulk stores per bin
     auto bkern = part_scatter32_bulk_kernel<KT>;
     const size_t bsmem = sizeof(Scatter32BulkSmem);
     B200_CUDA_TRY(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
@@ -1770,6 +1930,8 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
         reg.status = nullptr;
         reg.region_cap = cap;
         reg.overflow = d_overflow;
+        reg.counts = nullptr;
+        reg.offsets0 = nullptr;
         for (int r = 0; r < kMaxPeers; ++r) reg.base[r] = nullptr;
         reg.base[0] = ppairs.as<uint2>();
         e = partition_scatter32<KT, false>(probe_col, g, h_cursors, d_cursors, ppairs.as<uint2>(), nullptr, 0, &reg, false,
@@ -2061,8 +2223,8 @@ gdf_error xjoin_count(const gdf_column* key, unsigned ranks, unsigned nlocal, un
 // dst_pairs[r] = rank r's pair buffer as mapped on THIS device; h_offsets[r * nlocal + p] = position inside it of this
 // rank's first pair of local partition p.  Rows whose key does not fit 32 bits are dropped (they cannot match).
 gdf_error xjoin_scatter(const gdf_column* key, int32_t id_base, unsigned ranks, unsigned nlocal, void* const* dst_pairs,
-                        const unsigned long long* h_offsets, const int* d_status /* non-null: h_offsets is a DEVICE array */,
-                        int ctas_per_sm) {
+                        const unsigned long long* offsets, const unsigned long long* counts,
+                        const int* d_status /* non-null: offsets and counts are DEVICE arrays */, int ctas_per_sm) {
   B200_REQUIRE(ranks >= 1 && ranks <= (unsigned)kMaxPeers && nlocal >= 1 && (nlocal & (nlocal - 1)) == 0 &&
                    ranks * nlocal <= kMaxParts, GDF_INVALID_API_CALL);
   const PartGeom g = combined_geom(ranks, nlocal);
@@ -2073,14 +2235,25 @@ gdf_error xjoin_scatter(const gdf_column* key, int32_t id_base, unsigned ranks, 
   peer.region_cap = 0;
   peer.overflow = nullptr;
   for (int r = 0; r < kMaxPeers; ++r) peer.base[r] = r < (int)ranks ? static_cast<uint2*>(dst_pairs[r]) : nullptr;
-  Scratch small;
-  B200_CUDA_TRY(small.alloc((size_t)g.nparts * sizeof(unsigned long long)));
-  const bool dev = d_status != nullptr;  // offsets are a device array (asynchronous exchange)
+  Scratch small;  // cursors[np] | tail cursors[np] | counts[np] | offsets[np]
+  B200_CUDA_TRY(small.alloc((size_t)g.nparts * 4 * sizeof(unsigned long long)));
+  const bool dev = d_status != nullptr;  // asynchronous exchange: the plan lives on the device
+  if (dev) {
+    peer.counts = counts;
+    peer.offsets0 = offsets;
+  } else {  // host plan: the kernel still wants its own device copies (the cursors are consumed)
+    unsigned long long* d_counts = small.as<unsigned long long>() + 2 * (size_t)g.nparts;
+    unsigned long long* d_off0 = d_counts + g.nparts;
+    B200_CUDA_TRY(cudaMemcpy(d_counts, counts, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpy(d_off0, offsets, g.nparts * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    peer.counts = d_counts;
+    peer.offsets0 = d_off0;
+  }
   switch (key->dtype) {
     case GDF_INT64: case GDF_DATE64: case GDF_TIMESTAMP:
-      return partition_scatter32<uint64_t, false>(key, g, h_offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer, dev, ctas_per_sm);
+      return partition_scatter32<uint64_t, false>(key, g, offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer, dev, ctas_per_sm);
     case GDF_INT32: case GDF_DATE32:
-      return partition_scatter32<uint32_t, false>(key, g, h_offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer, dev, ctas_per_sm);
+      return partition_scatter32<uint32_t, false>(key, g, offsets, small.as<unsigned long long>(), nullptr, nullptr, id_base, &peer, dev, ctas_per_sm);
     default: return GDF_UNSUPPORTED_DTYPE;
   }
 }
@@ -2126,8 +2299,8 @@ __global__ void xjoin_plan_kernel(const unsigned long long* __restrict__ all, un
   for (unsigned side = 0; side < 2; ++side) {
     unsigned long long before_me = 0, total = 0;
     if (b < bins)
-      for (unsigned s = 0; s < ranks; ++s) {
-        const unsigned long long c = all[(size_t)s * stride + side * (bins + 1) + b];
+      for (unsigned s = 0; s < ranks; ++s) {  // every (sender, bin) slot holds whole 32-byte granules (part_scatter32_even_kernel)
+        const unsigned long long c = (all[(size_t)s * stride + side * (bins + 1) + b] + kXG - 1) & ~(unsigned long long)(kXG - 1);
         if (s < rank) before_me += c;
         total += c;
       }

@@ -137,11 +137,12 @@ class GdfOps(object):
         lib.gdfx_xjoin_count(self.C.Column(keys).cdata, ranks, nlocal, counts, hi)
         return [int(counts[i]) for i in range(ranks * nlocal)], int(hi[0])
 
-    def xjoin_scatter(self, keys, id_base, ranks, nlocal, dst_ptrs, offsets):
+    def xjoin_scatter(self, keys, id_base, ranks, nlocal, dst_ptrs, offsets, counts):
         ffi, lib = self.ffi, self.lib
         dp = ffi.new("void*[]", [ffi.cast("void*", p) for p in dst_ptrs])
         off = ffi.new("unsigned long long[]", [int(o) for o in offsets])
-        lib.gdfx_xjoin_scatter(self.C.Column(keys).cdata, id_base, ranks, nlocal, dp, off)
+        cnt = ffi.new("unsigned long long[]", [int(c) for c in counts])
+        lib.gdfx_xjoin_scatter(self.C.Column(keys).cdata, id_base, ranks, nlocal, dp, off, cnt)
 
     def xjoin_count_dev(self, keys, ranks, nlocal, d_counts):
         self.lib.gdfx_xjoin_count_dev(self.C.Column(keys).cdata, ranks, nlocal, self.ffi.cast("unsigned long long*", d_counts.data_ptr()))
@@ -152,11 +153,12 @@ class GdfOps(object):
                                      c("unsigned long long*", d_off_build.data_ptr()), c("unsigned long long*", d_off_probe.data_ptr()),
                                      c("int*", d_status.data_ptr()))
 
-    def xjoin_scatter_dev(self, keys, id_base, ranks, nlocal, dst_ptrs, d_offsets, d_status, ctas_per_sm=0):
+    def xjoin_scatter_dev(self, keys, id_base, ranks, nlocal, dst_ptrs, d_offsets, d_counts, d_status, ctas_per_sm=0):
         ffi, lib = self.ffi, self.lib
         dp = ffi.new("void*[]", [ffi.cast("void*", p) for p in dst_ptrs])
         lib.gdfx_xjoin_scatter_dev(self.C.Column(keys).cdata, id_base, ranks, nlocal, dp,
-                                   ffi.cast("unsigned long long*", d_offsets.data_ptr()), ffi.cast("int*", d_status.data_ptr()),
+                                   ffi.cast("unsigned long long*", d_offsets.data_ptr()),
+                                   ffi.cast("unsigned long long*", d_counts.data_ptr()), ffi.cast("int*", d_status.data_ptr()),
                                    ctas_per_sm)
 
     def xjoin_build(self, build_ptr, build_counts, nlocal, overlap):
@@ -420,8 +422,8 @@ class PeerExchange(object):
             return None
         sb, sp = self._ensure_pairs("xbuild", max(recv_b)), self._ensure_pairs("xprobe", max(recv_p))
         ev.mark("count+plan")
-        self.ops.xjoin_scatter(build_keys, build_offset, world, nlocal, sb["peers"][0], off_b)
-        self.ops.xjoin_scatter(probe_keys, probe_offset, world, nlocal, sp["peers"][0], off_p)
+        self.ops.xjoin_scatter(build_keys, build_offset, world, nlocal, sb["peers"][0], off_b, cb)
+        self.ops.xjoin_scatter(probe_keys, probe_offset, world, nlocal, sp["peers"][0], off_p, cp)
         if self._flag is None:
             self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         dist.all_reduce(self._flag, group=self.group)                 # stream-ordered: every rank's stores have landed
@@ -461,21 +463,21 @@ class PeerExchange(object):
         ev.mark("count+plan")
         if self._flag is None:
             self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.ops.xjoin_scatter_dev(build_keys, build_offset, world, nlocal, sb["peers"][0], off[:bins], status)
+        self.ops.xjoin_scatter_dev(build_keys, build_offset, world, nlocal, sb["peers"][0], off[:bins], mine[:bins], status)
         dist.all_reduce(self._flag, group=self.group)                 # stream-ordered: every rank's BUILD pairs have landed
         copied.synchronize()                                          # long done: the copy only waited for the all_gather
         M = st["pin"][:world * stride].view(world, stride).numpy()
         wide, overflow = int(st["pin"][world * stride]), int(st["pin"][world * stride + 1])
         if wide or overflow:                                          # nothing was / will be written (the scatters check the flags)
             return None if wide else False                            # two-pass path / synchronous route that grows the buffers
-        tot_b = M[:, rank * nlocal:(rank + 1) * nlocal].sum(0)
-        tot_p = M[:, bins + 1 + rank * nlocal:bins + 1 + (rank + 1) * nlocal].sum(0)
+        tot_b = _granules(M[:, rank * nlocal:(rank + 1) * nlocal]).sum(0)          # slots are padded (plan_fused_exchange)
+        tot_p = _granules(M[:, bins + 1 + rank * nlocal:bins + 1 + (rank + 1) * nlocal]).sum(0)
         if int(tot_b.max()) > (1 << 22):
             return None
         # tables are filled on a private stream while the probe side crosses NVLink on this one
         handle = self.ops.xjoin_build(sb["mine"][0], tot_b.tolist(), nlocal, self.overlap_build)
-        self.ops.xjoin_scatter_dev(probe_keys, probe_offset, world, nlocal, sp["peers"][0], off[bins:], status,
-                                   self.scatter_ctas_per_sm if self.overlap_build else 0)
+        self.ops.xjoin_scatter_dev(probe_keys, probe_offset, world, nlocal, sp["peers"][0], off[bins:], mine[bins + 1:2 * bins + 1],
+                                   status, self.scatter_ctas_per_sm if self.overlap_build else 0)
         dist.all_reduce(self._flag, group=self.group)                 # every rank's PROBE pairs have landed
         ev.mark("partition+exchange")
         out = self.ops.xjoin_probe(handle, sp["mine"][0], tot_p.tolist())
@@ -502,14 +504,24 @@ class PeerExchange(object):
         return self.ops.view(slot["mine"][0], n, np_key), self.ops.view(slot["mine"][1], n, np.int32)
 
 
+EXCHANGE_GRANULE = 4      # pairs per 32-byte sector: csrc/join_part.cu kXG
+
+
+def _granules(c):
+    """Counts rounded up to whole exchange granules (numpy array or int)."""
+    return (c + EXCHANGE_GRANULE - 1) & ~(EXCHANGE_GRANULE - 1)
+
+
 def plan_fused_exchange(counts, world, nlocal, rank):
     """Host-side plan of the one-pass exchange.  counts[s][d * nlocal + p] = pairs rank s sends to (rank d, local
     partition p).  Receiver d lays its buffer out partition-major, and inside a partition in sender order, so
         offsets[d * nlocal + p]  where THIS rank's pairs of bin (d, p) start inside d's buffer
-        part_totals[p]           pairs of local partition p this rank receives (all senders)
+        part_totals[p]           pairs of local partition p this rank receives (all senders, pads included)
         recv_rows[d]             total pairs rank d receives (buffer sizing)
+    Slots are padded to whole 32-byte granules so that the scatter sends nothing but sector-aligned bulk stores over NVLink.
     Pure arithmetic on the gathered count matrix: every rank computes the same plan (tests/test_dist_cpu.py)."""
     c = np.asarray(counts, dtype=np.int64).reshape(world, world * nlocal)
+    c = _granules(c)      # every (sender, bin) slot holds whole 32-byte granules: the rest is padded with "no row" pairs
     totals = c.sum(0)                                             # pairs of every bin, all senders
     before_me = c[:rank].sum(0)                                   # ... of the senders ranked before this one
     bin_start = (np.cumsum(totals.reshape(world, nlocal), 1) - totals.reshape(world, nlocal)).reshape(-1)   # inside its destination

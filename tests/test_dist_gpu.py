@@ -191,13 +191,16 @@ def test_one_pass_fused_exchange_matches_oracle(world, nlocal, key_dtype):
     buf_b = [torch.full((plans_b[0][2][d] + pad, 2), -7, dtype=torch.int32, device="cuda") for d in range(world)]
     buf_p = [torch.full((plans_p[0][2][d] + pad, 2), -7, dtype=torch.int32, device="cuda") for d in range(world)]
     for r, (pk, plo, bk, blo) in enumerate(shards):
-        ops.xjoin_scatter(bk, blo, world, nlocal, [t.data_ptr() for t in buf_b], plans_b[r][0])
-        ops.xjoin_scatter(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], plans_p[r][0])
+        ops.xjoin_scatter(bk, blo, world, nlocal, [t.data_ptr() for t in buf_b], plans_b[r][0], counts_b[r])
+        ops.xjoin_scatter(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], plans_p[r][0], counts_p[r])
     torch.cuda.synchronize()
     got_l, got_r = [], []
     for d in range(world):
         assert (buf_b[d][-pad:] == -7).all() and (buf_p[d][-pad:] == -7).all()          # nothing written past the plan
-        assert (buf_b[d][:-pad, 1] >= 0).all() and (buf_p[d][:-pad, 1] >= 0).all()      # no hole left inside it
+        INT_MIN = -(1 << 31)                                                             # the "no row" pad of an odd slot
+        for buf in (buf_b[d], buf_p[d]):                                                  # no hole left inside the plan
+            tags = buf[:-pad, 1]
+            assert bool(((tags >= 0) | (tags == INT_MIN)).all()) and int((tags == INT_MIN).sum()) <= 3 * world * nlocal
         gl, gr = ops.xjoin_local(buf_p[d].data_ptr(), plans_p[d][1], buf_b[d].data_ptr(), plans_b[d][1], nlocal)
         got_l.append(gl.cpu().numpy()), got_r.append(gr.cpu().numpy())
     gl, gr = np.concatenate(got_l), np.concatenate(got_r)
@@ -251,21 +254,24 @@ def test_device_side_exchange_plan_equals_host_plan(world, nlocal):
         # too small a buffer: flagged, and the scatter leaves the buffers untouched
         ops.xjoin_plan_dev(allc, world, nlocal, r, cap_b, cap_p - 1, off[:bins], off[bins:], status)
         assert status.cpu().tolist() == [0, 1]
+        mine_r = allc[r * stride:(r + 1) * stride]
         if r == 0:                                   # nothing has been written yet
-            ops.xjoin_scatter_dev(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], off[bins:], status)
+            ops.xjoin_scatter_dev(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], off[bins:], mine_r[bins + 1:2 * bins + 1], status)
             assert all(bool((t == -7).all()) for t in buf_p)
         ops.xjoin_plan_dev(allc, world, nlocal, r, cap_b, cap_p, off[:bins], off[bins:], status)
         assert status.cpu().tolist() == [0, 0]
         want_b, want_p = D.plan_fused_exchange(counts_b, world, nlocal, r)[0], D.plan_fused_exchange(counts_p, world, nlocal, r)[0]
         assert off.cpu().tolist() == want_b + want_p
-        ops.xjoin_scatter_dev(bk, blo, world, nlocal, [t.data_ptr() for t in buf_b], off[:bins], status)
-        ops.xjoin_scatter_dev(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], off[bins:], status)
+        ops.xjoin_scatter_dev(bk, blo, world, nlocal, [t.data_ptr() for t in buf_b], off[:bins], mine_r[:bins], status)
+        ops.xjoin_scatter_dev(pk, plo, world, nlocal, [t.data_ptr() for t in buf_p], off[bins:], mine_r[bins + 1:2 * bins + 1], status)
     torch.cuda.synchronize()
     got_l, got_r = [], []
     for d in range(world):
         tot_b = D.plan_fused_exchange(counts_b, world, nlocal, d)[1]
         tot_p = D.plan_fused_exchange(counts_p, world, nlocal, d)[1]
-        assert bool((buf_b[d][:recv_b[d], 1] >= 0).all()) and bool((buf_p[d][:recv_p[d], 1] >= 0).all())
+        for buf, rows in ((buf_b[d], recv_b[d]), (buf_p[d], recv_p[d])):              # filled completely: real pairs or pad pairs
+            tags = buf[:rows, 1]
+            assert bool(((tags >= 0) | (tags == -(1 << 31))).all())
         if d % 2:      # the two-stage form: tables filled on the library's private stream, then the probe waits for them
             handle = ops.xjoin_build(buf_b[d].data_ptr(), tot_b, nlocal, True)
             gl, gr = ops.xjoin_probe(handle, buf_p[d].data_ptr(), tot_p)

@@ -46,12 +46,12 @@ __global__ void store_split(unsigned char* local, unsigned char* remote, size_t 
 
 // "bulk": the same runs written by the TMA engine - one cp.async.bulk shared -> global per run, issued by one lane.
 __global__ void store_bulk(unsigned char* local, unsigned char* remote, size_t total_bytes, unsigned run_bytes, unsigned remote_num,
-                           unsigned remote_den) {
+                           unsigned remote_den, unsigned extra_plain = 0, unsigned shift_bytes = 0, unsigned stride_bytes = 0) {
   extern __shared__ __align__(128) unsigned char stage[];
   for (unsigned i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<unsigned*>(stage)[i] = i;
   __syncthreads();
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  const size_t runs = total_bytes / run_bytes;
+  const size_t runs = total_bytes / (stride_bytes ? stride_bytes : run_bytes);
   const unsigned lane = threadIdx.x & 31u, warp_in_cta = threadIdx.x >> 5;
   const size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
@@ -59,8 +59,14 @@ __global__ void store_bulk(unsigned char* local, unsigned char* remote, size_t t
   for (size_t r = warp * 32 + lane; r < runs; r += warps * 32, ++n) {   // every lane issues its own run
     const size_t slot = (r * 2654435761ull) % runs;
     const bool to_remote = (r % remote_den) < remote_num;
-    unsigned char* dst = (to_remote ? remote : local) + slot * run_bytes;
+    unsigned char* dst = (to_remote ? remote : local) + slot * (stride_bytes ? stride_bytes : run_bytes) + shift_bytes;
     const unsigned src = (unsigned)__cvta_generic_to_shared(stage + ((r * run_bytes) & 16383u & ~15u));
+    if (extra_plain) {  // the join scatter's odd head / tail pairs: plain 8-byte stores next to the bulk store
+      const unsigned body = run_bytes - 16;
+      *reinterpret_cast<uint2*>(dst) = make_uint2((unsigned)r, 1u);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + 16), "r"(src), "r"(body) : "memory");
+      if (extra_plain > 1) *reinterpret_cast<uint2*>(dst + 8) = make_uint2((unsigned)r, 2u);
+    } else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(run_bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     if ((n & 7u) == 7u) asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
@@ -149,6 +155,30 @@ int main() {
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
       printf("%-6u %u/%-8u %-9.3f %-9.0f %-12.0f\n", rs, num[mix], den[mix], ms, bytes / ms / 1e6, bytes / ms / 1e6 * num[mix] / den[mix]);
+    }
+  printf("\nbulk + plain 8-byte head/tail stores per run (one direction)\n%-8s %-6s %-10s %-9s %-12s\n", "plain", "run_B", "remote", "ms", "GB/s remote");
+  for (unsigned extra = 0; extra <= 2; ++extra)
+    for (unsigned rs : {256u, 512u}) {
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      store_bulk<<<148 * 4, 256, 32768>>>(local, remote, bytes, rs, 1, 2, extra);
+      CK(cudaDeviceSynchronize());
+      cudaEventRecord(e0);
+      for (int i = 0; i < 3; ++i) store_bulk<<<148 * 4, 256, 32768>>>(local, remote, bytes, rs, 1, 2, extra);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
+      printf("%-8u %-6u 1/2        %-9.3f %-12.0f\n", extra, rs, ms, bytes / ms / 1e6 / 2);
+    }
+  printf("\nbulk stores whose runs are not line-aligned (slots 512 B apart, 1/2 remote)\n%-8s %-8s %-9s %-14s\n", "run_B", "shift_B", "ms", "GB/s remote (payload)");
+  for (unsigned rs : {256u, 272u, 320u})
+    for (unsigned sh : {0u, 16u, 32u, 64u}) {
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      store_bulk<<<148 * 4, 256, 32768>>>(local, remote, bytes, rs, 1, 2, 0, sh, 512);
+      CK(cudaDeviceSynchronize());
+      cudaEventRecord(e0);
+      for (int i = 0; i < 3; ++i) store_bulk<<<148 * 4, 256, 32768>>>(local, remote, bytes, rs, 1, 2, 0, sh, 512);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
+      printf("%-8u %-8u %-9.3f %-14.0f\n", rs, sh, ms, (double)(bytes / 512) * rs / ms / 1e6 / 2);
     }
   // ---- both directions at once: GPU 0 -> 1 and GPU 1 -> 0 (what an all-to-all exchange does) ----
   {
