@@ -793,16 +793,17 @@ def csrc_sha1():
     return h.hexdigest()
 
 
-def measured_traffic(workload_key, kernel, scale):
-    """DRAM bytes per launch from the full-size ncu capture (tools/traffic_full.sh -> profiles/r02_traffic_full_size.json).
-    The file records the hash of csrc/ it was captured from; a record from other sources is stale and is NOT reported."""
+def measured_traffic(workload_key, kernel, scale, launches_per_step=1.0):
+    """DRAM bytes per launch (per-step bytes of everything timed under `kernel` / its launches per step) from the full-size
+    ncu capture (tools/traffic_full.sh -> profiles/r02_traffic_full_size.json).  The file records the hash of csrc/ it was
+    captured from; a record from other sources is stale and is NOT reported."""
     if scale != 1.0 or not os.path.isfile(TRAFFIC_FILE):
         return None
     data = json.load(open(TRAFFIC_FILE))
     if data.get("csrc_sha1") != csrc_sha1():
         return None
     rec = data.get("entries", {}).get(workload_key, {}).get(kernel)
-    return (rec["dram_read"] + rec["dram_write"]) if rec else None
+    return int((rec["dram_read"] + rec["dram_write"]) / max(launches_per_step, 1e-9)) if rec else None
 
 
 def roofline_for(res, wl, peak_gbs, peak_kind, scale=1.0, key=None):
@@ -816,7 +817,7 @@ def roofline_for(res, wl, peak_gbs, peak_kind, scale=1.0, key=None):
         return {"kernel": top, "bound": "hbm", "achieved": None, "peak": peak_gbs, "unit": "GB/s", "frac": None, "traffic": None}
     achieved = nbytes / 1e9 / (per_launch_ms * 1e-3)
     return {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": measured_traffic(key, top, scale), "peak_source": peak_kind,
+            "frac": achieved / peak_gbs, "traffic": measured_traffic(key, top, scale, ks[top]["launches_per_step"]), "peak_source": peak_kind,
             "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": per_launch_ms,
             "share_of_step": ks[top]["ms_per_step"] / res["ms_per_step"]}
 

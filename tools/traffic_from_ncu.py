@@ -16,7 +16,7 @@ import bench  # noqa: E402
 TIMER = [(r"probe32|part_probe", "join_part_probe"), (r"build32|part_build_kernel", "join_part_build"), (r"part_hist", "join_part_hist"),
          (r"part_scatter", "join_part_scatter"), (r"fixup", "join_output_fixup"), (r"build_fast", "groupby_build_fast"),
          (r"extract_fast", "groupby_extract"), (r"select_stream|select_chunked|select_kernel", "select"), (r"compare_static", "compare_static"),
-         (r"reduce_kernel", "reduce"), (r"binary_", "binary_op"), (r"partition_(hist|scan|scatter)_kernel", "hash_partition"),
+         (r"reduce_kernel<(long|int|short|signed char|float|double), ", "reduce"), (r"binary_", "binary_op"), (r"partition_(hist|scan|scatter)_kernel", "hash_partition"),
          (r"gather_kernel", "join_gather")]
 
 
@@ -44,11 +44,11 @@ def main():
             a["dram_write"] += m.get("dram__bytes_write.sum", 0)
             a["ncu_time_ns"] += m.get("gpu__time_duration.sum", 0)
             a["launches"] += 1
-        # per LAUNCH of the timer's dominant kernel: timers that bracket several launches (two scatters) report the mean
-        entries[key] = {t: {"dram_read": int(a["dram_read"] / a["launches"]), "dram_write": int(a["dram_write"] / a["launches"]),
-                            "ncu_time_ns": int(a["ncu_time_ns"] / a["launches"]), "launches_in_capture": a["launches"]}
+        # per STEP: the capture holds exactly two calls of the workload (its parity check + one timed step)
+        entries[key] = {t: {"dram_read": int(a["dram_read"] / 2), "dram_write": int(a["dram_write"] / 2),
+                            "ncu_time_ns": int(a["ncu_time_ns"] / 2), "kernel_launches_per_step": a["launches"] / 2.0}
                         for t, a in agg.items()}
-    json.dump({"_comment": "DRAM bytes per launch at FULL BASELINE size (ncu single-pass counters, one bench step per workload, "
+    json.dump({"_comment": "DRAM bytes per STEP (all kernels under one bench.py timer name) at FULL BASELINE size (ncu single-pass counters, "
                            "tools/traffic_full.sh). bench.py reports roofline.traffic from here only while csrc_sha1 matches the sources.",
                "csrc_sha1": bench.csrc_sha1(), "entries": entries}, sys.stdout, indent=1)
 
