@@ -32,11 +32,8 @@ if has list; then
   done
 fi
 if has traffic; then
-  # DRAM bytes of the dominant kernels at FULL size (single-pass counters, no kernel replay)
-  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k regex:'part_probe|build_fast|select_stream' --csv --log-file $OUT/traffic_full.csv \
-    python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > $OUT/traffic_full.log 2>&1
-  echo "traffic rc=$?"
+  # DRAM bytes of every library kernel at FULL size (single-pass counters, no kernel replay) -> gpurun_out/r02_traffic_full_size.json
+  bash tools/traffic_full.sh
 fi
 if has full; then
   # quarter-size inputs: ncu's kernel replay saves/restores every written allocation; the partition
