@@ -93,13 +93,16 @@ struct Scratch {  // RAII wrapper; frees in stream order
 };
 
 // Optional per-kernel timing (gdfx_profile_enable / gdfx_profile_report, include/gdf_b200_ext.h).
-// B200_TIMED("name") brackets the launches in the enclosing scope with events on stream 0.
+// B200_TIMED("name") brackets the launches in the enclosing scope with events on stream 0 (B200_TIMED_ON: on the
+// given stream - work that runs on the library's private stream beside the legacy stream).
 struct KernelTimer {
-  explicit KernelTimer(const char* name);
+  explicit KernelTimer(const char* name, cudaStream_t s = 0);
   ~KernelTimer();
   int slot;
+  cudaStream_t stream;
 };
 #define B200_TIMED(name) ::b200::KernelTimer b200_kernel_timer__(name)
+#define B200_TIMED_ON(name, s) ::b200::KernelTimer b200_kernel_timer__(name, s)
 
 // Lab knobs: A/B switches of kernel variants for tools/lab_*.py.  The shipped library has ONE behaviour: unless
 // it is built with -DB200_LAB (make LAB=1 -> lib_lab/), a knob is its compile-time default and no environment

@@ -1890,7 +1890,10 @@ gdf_error run_partitioned(int kind, const gdf_column* probe_col, const gdf_colum
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(side, issued, 0);
         cudaEventDestroy(issued);
         if (ce != cudaSuccess) return GDF_CUDA_ERROR;
-        e = compact_build(g, bp32, h_btot, d_toffset, d_tmask, d_flags, table, &t, side);
+        {
+          B200_TIMED_ON("join_part_build", side);   // elapsed time on the private stream: it overlaps the probe-side scatter
+          e = compact_build(g, bp32, h_btot, d_toffset, d_tmask, d_flags, table, &t, side);
+        }
         if (e == GDF_SUCCESS && (cudaEventCreateWithFlags(&built, cudaEventDisableTiming) != cudaSuccess ||
                                  cudaEventRecord(built, side) != cudaSuccess))
           e = GDF_CUDA_ERROR;
@@ -2393,6 +2396,7 @@ gdf_error xjoin_build(const void* build_pairs, const unsigned long long* build_c
   if (e == GDF_SUCCESS && build_rows) {
     const Pairs32 bp{static_cast<const uint2*>(build_pairs), (size_t)build_rows};
     if (side) {
+      B200_TIMED_ON("join_part_build", s);
       e = compact_build(h->g, bp, build_counts, d_toffset, d_tmask, h->d_flags, h->table, &h->t, s);
     } else {
       B200_TIMED("join_part_build");

@@ -119,13 +119,13 @@ Profiler& prof() {
 }
 }  // namespace
 
-KernelTimer::KernelTimer(const char* name) : slot(-1) {
+KernelTimer::KernelTimer(const char* name, cudaStream_t s) : slot(-1), stream(s) {
   Profiler& p = prof();
   if (!p.enabled) return;
   std::lock_guard<std::mutex> g(p.mu);
   Pending pe{name, p.get(), p.get()};
   if (!pe.start || !pe.stop) return;
-  cudaEventRecord(pe.start, 0);
+  cudaEventRecord(pe.start, stream);
   slot = (int)p.pending.size();
   p.pending.push_back(pe);
 }
@@ -133,7 +133,7 @@ KernelTimer::~KernelTimer() {
   if (slot < 0) return;
   Profiler& p = prof();
   std::lock_guard<std::mutex> g(p.mu);
-  if (slot < (int)p.pending.size()) cudaEventRecord(p.pending[slot].stop, 0);
+  if (slot < (int)p.pending.size()) cudaEventRecord(p.pending[slot].stop, stream);
 }
 
 }  // namespace b200
