@@ -6,25 +6,33 @@ Exactly ONE JSON line on stdout (anything a library prints to fd 1 is diverted t
 N = 1   headline = BASELINE.json's metric "rows/sec hash inner-join ... int64": C3 = gdf_inner_join of 1e9
         probe rows x 1e8 build rows, int64 keys (build = permutation, probe uniform, every probe row matches
         once).  A step = one gdf_inner_join call over device-resident columns + gdf_column_free of its outputs.
-        The same line carries C4 gdf_group_by_sum (1e9 rows, 1e6 int64 groups, Zipf s=1.05) and C2 gdf_filter
-        (1e9 int64 rows, 10 % selectivity) under `workloads`, each with its own roofline object.
+        The same line carries, under `workloads` and each with its own roofline object and full-size parity
+        properties: C4 gdf_group_by_sum (1e9 rows, 1e6 int64 groups, Zipf s=1.05; uniform-key variants), C2
+        gdf_filter (1e9 int64 rows, 10 % selectivity) and its gpu_comparison_static + gpu_apply_stencil variant,
+        gdf_sum_i64 (plain / masked), gdf_add (C1 and 2.5e8 int64 rows), gdf_hash_partition, a join with
+        result_cols, and C5 (left join, composite key, 30 % null rows) on one GPU.
   value      rows/s (probe+build rows per step / CUDA-event time), inputs resident in HBM
-  e2e        the same C-ABI call from pinned HOST buffers: H2D of both key columns and D2H of both index
-             columns inside the timed region (PCIe-bound)
+  e2e        the same C-ABI call from pinned HOST buffers as ONE call: H2D of both key columns and D2H of both
+             index columns inside the timed region (PCIe-bound); e2e.pipelined = the probe column streamed
+             through the same call in 8 pieces with the copies overlapped
   roofline   dominant kernel of the headline step: algorithmic bytes of that kernel / its average launch
              duration (CUDA events recorded by the library around every launch, live in the timed steps)
-             vs MEASURED_PEAKS.json hbm_gbs; traffic = DRAM bytes per launch from the committed full-size
-             ncu capture (profiles/r01c_traffic_full_size.json)
-  cpu_baseline  the C oracle port (single thread) on a bounded sample of C3
+             vs MEASURED_PEAKS.json hbm_gbs; traffic = DRAM bytes per launch from the full-size ncu capture
+             (profiles/r02_traffic_full_size.json, reported only while the SHA-1 of csrc/ it was captured from
+             matches the sources: tools/traffic_full.sh regenerates it)
+  cpu_baseline  the C oracle port (single thread) on a bounded sample of C3; cpu_baseline_pyarrow beside it
 N > 1   (torchrun) strong scaling of C3: the two tables are block-distributed over the ranks; every step
-        partitions both sides by destination rank INSIDE one kernel that stores the rows into the peers'
-        receive buffers over NVLink (--exchange p2p, default; falls back to hash-partition + NCCL all_to_all
-        when CUDA IPC peer mapping is unavailable, or with --exchange nccl), then joins locally.  Time = max
-        over ranks of the CUDA-event time between two barriers.
+        partitions both sides by (destination rank x the receiver's local partition) INSIDE one kernel that
+        stores the rows into the peers' partition-contiguous receive buffers over NVLink (--exchange p2p,
+        default; hash-partition + NCCL all_to_all when CUDA IPC peer mapping is unavailable or with
+        --exchange nccl), then builds and probes locally.  Time = max over ranks of the CUDA-event time between
+        two barriers.  The same launch then times C4 (two-phase distributed group-by) and C5 (distributed left
+        join on the composite key with NULLs) under `workloads`, with per-phase device times.
 --impl reference   the reference's own kernels (oracle/_ref/libgdf_ref.so = gpuopenanalytics/libgdf rebuilt for
         sm_100a; the reference is a CUDA library and has no CPU implementation) through the identical harness
-        on a bounded sample (1/10 of the rows; 5e6 rows for its group-by, whose CAS loop serialises on the
-        Zipf hot key).  Under torchrun only rank 0 runs it.
+        on the SAME config: C3 at 1e9 x 1e8 and C2 at 1e9 rows.  Only its group-by is bounded (5e8 rows with
+        uniform keys - its int arithmetic overflows above 2^29 rows - and a 5e6-row Zipf sample: its CAS loop
+        serialises on the hot key).  Under torchrun only rank 0 runs it.
 """
 import argparse
 import json
